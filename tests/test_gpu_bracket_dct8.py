@@ -1,0 +1,80 @@
+"""GPU: colour bracket and the 8x8 DCT pair vs the oracle (cv2 / reference restatement)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bracket, dct8 as o_dct, dwt_dct_svd as o_svd, payload as o_pay, synth
+from parity import PAYLOAD, KEY
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_colour_bracket_is_bit_exact_vs_opencv():
+    from b200wm import ops
+    rng = np.random.RandomState(0)
+    for shape in ((240, 320, 3), (128, 512, 3), (37, 53, 3), (1080, 1920, 3)):
+        frame = rng.randint(0, 256, shape).astype(np.uint8)
+        want = bracket.to_yuv(frame)
+        got = ops.bgr8_to_yuv32(torch.from_numpy(frame).to(DEV)).cpu().numpy()
+        w16 = shape[1] // 16 * 16          # OpenCV's scalar tail (width % vector) is not fused; compare the vector body
+        assert np.array_equal(got[:, :w16], want[:, :w16])
+        np.testing.assert_allclose(got, want, rtol=0, atol=3e-5)
+        yuv = want + rng.normal(0, 3, shape).astype(np.float32)
+        want8 = bracket.from_yuv(yuv.copy())
+        got8 = ops.yuv32_to_bgr8(torch.from_numpy(yuv).to(DEV)).cpu().numpy()
+        assert np.abs(got8[:, :w16].astype(np.int16) - want8[:, :w16]).max() == 0
+        assert np.abs(got8.astype(np.int16) - want8).max() <= 1
+
+
+def _masks_oracle(lum):
+    coeffs = o_dct._dct_all(lum)
+    return coeffs[..., 0, 0] / 8, o_dct.texture_mask_from_coeffs(coeffs), o_dct.luminance_mask_from_dc(coeffs[..., 0, 0])
+
+
+def test_dct8_masks_vs_oracle(golden_dir):
+    from b200wm import ops
+    g = np.load(os.path.join(golden_dir, "frame63_crop.npz"))
+    for frame in (g["bgr"], synth.random_bgr(100, 132, 9), synth.random_bgr(64, 64, 3)):
+        yuv = bracket.to_yuv(frame)
+        mean_o, tex_o, lum_o = _masks_oracle(yuv[:, :, 0])
+        block_mean, tex, frame_sum = ops.dct8_masks(torch.from_numpy(yuv).to(DEV), channel=0)
+        np.testing.assert_allclose(block_mean[0].cpu().numpy(), mean_o.reshape(-1), rtol=2e-6, atol=2e-5)
+        np.testing.assert_allclose(float(frame_sum[0]), mean_o.astype(np.float64).sum(), rtol=1e-6)
+        tex_g = tex[0].cpu().numpy().reshape(tex_o.shape)
+        agree = np.isclose(tex_g, tex_o, rtol=1e-5, atol=1e-6)
+        assert agree.mean() > 0.995, f"texture mask agreement {agree.mean()}"
+
+
+@pytest.mark.parametrize("source", ["frame63", "synthetic"])
+def test_dct8_embed_extract_vs_oracle(golden_dir, source):
+    from b200wm import ops
+    if source == "frame63":
+        frame = np.load(os.path.join(golden_dir, "frame63_crop.npz"))["bgr"]
+    else:
+        frame = synth.random_bgr(128, 192, 21)
+    yuv0 = bracket.to_yuv(frame)
+    wm = o_pay.generate_wm(PAYLOAD, o_svd.wm_capacity(frame.shape), KEY)
+    want = o_dct.encode(yuv0.copy(), wm)
+    t = torch.from_numpy(yuv0).to(DEV)
+    packed, n = ops.pack_bits(wm[0], device=DEV)
+    masks = ops.dct8_masks(t, channel=0)
+    ops.dct8_embed_(t, masks, packed, n, alpha=20, channel=1)
+    got = t.cpu().numpy()
+    assert np.array_equal(got[:, :, 0], yuv0[:, :, 0]) and np.array_equal(got[:, :, 2], yuv0[:, :, 2])
+    # per-block agreement: a block can only differ when a mask threshold or the floor() in the
+    # quantiser is decided by float32 rounding inside cv2.dct; those are rare
+    by, bx = frame.shape[0] // 8, frame.shape[1] // 8
+    err = np.abs(got[:by * 8, :bx * 8, 1] - want[:by * 8, :bx * 8, 1]).reshape(by, 8, bx, 8).max(axis=(1, 3))
+    assert (err < 2e-3).mean() > 0.995, f"block agreement {(err < 2e-3).mean()}"
+    # extraction: our extractor on the reference's marked frame, and the reference's on ours
+    bits_ref = o_dct.decode(want.copy())
+    tw = torch.from_numpy(want).to(DEV)
+    raw, counts = ops.dct8_extract(tw, ops.dct8_masks(tw, channel=0), alpha=20, payload_len=8, channel=1)
+    bits = ops.unpack_bits(raw, bits_ref.size)
+    assert (bits == bits_ref).mean() > 0.995
+    assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), o_pay.degenerate(bits_ref, 8, KEY))
+    assert np.array_equal(o_pay.degenerate(o_dct.decode(got.copy()), 8, KEY), PAYLOAD)
+    assert counts[0].cpu().tolist() == [int(bits[0][i::8].sum()) for i in range(8)]

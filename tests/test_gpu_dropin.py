@@ -1,0 +1,129 @@
+"""GPU: the reference's driver flows running on the drop-in plugin classes
+(tests/mark.py + tests/detect.py, tests/test.py combos 0:0 / 0:3 / 1:0, HLS pattern collector)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bracket, dwt_dct_svd as o_svd, payload as o_pay
+from parity import PAYLOAD, KEY
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mark_py_and_detect_py_flow_on_in_mp4_frames(golden_dir):
+    """mark.py:18-40 then detect.py:17-31 with the in-memory reader/writer."""
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.extract.dwt_dct_svd_decoder import DwtDctSvdDecoder
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.degenerator.de_shuffler import DeShuffler
+    from offmark_b200.video.embedder import Embedder
+    from offmark_b200.video.extractor import Extractor
+    from offmark_b200.video.memory_io import ArrayReader, ArrayWriter
+
+    g = np.load(os.path.join(golden_dir, "in_mp4_frames.npz"))
+    frames = [g[f"rgb_{i}"] for i in g["picks"]]
+    r, w = ArrayReader(frames), ArrayWriter()
+    frame_embedder = DwtDctSvdEncoder()
+    capacity = frame_embedder.wm_capacity((r.height, r.width, 3))
+    wm = Shuffler(key=KEY).generate_wm(PAYLOAD, capacity)
+    assert np.array_equal(wm.astype(np.uint8), g["wm"])
+    frame_embedder.read_wm(wm)
+    Embedder(r, frame_embedder, w).start()
+    assert len(w.frames) == len(frames)
+    for i, src, marked in zip(g["picks"], frames, w.frames):
+        ref_marked = (src.astype(np.int16) + g[f"marked_minus_src_{i}"]).astype(np.uint8)
+        d = np.abs(marked.astype(np.int16) - ref_marked)
+        assert d.max() <= 1 and (d > 0).mean() < 2e-3, (d.max(), (d > 0).mean())
+
+    degenerator = DeShuffler(key=KEY).set_shape(PAYLOAD.shape)
+    extractor = Extractor(ArrayReader(w.frames), DwtDctSvdDecoder(), degenerator)
+    for i, marked in zip(g["picks"], w.frames):
+        assert np.array_equal(extractor.check_frame(marked), g["patterns_all_frames"][i])
+        # and on the reference's own marked frame: the per-frame pattern the reference reported
+        ref_marked = (g[f"rgb_{i}"].astype(np.int16) + g[f"marked_minus_src_{i}"]).astype(np.uint8)
+        assert np.array_equal(extractor.check_frame(ref_marked), g["patterns_all_frames"][i])
+    extractor.start()
+
+
+def test_test_py_flow_numpy_in_place_semantics(golden_dir):
+    """tests/test.py:85-121 with numpy frames: encode mutates and returns its argument."""
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.extract.dwt_dct_svd_decoder import DwtDctSvdDecoder
+    from offmark_b200.embed.dct_encoder import DctEncoder
+    from offmark_b200.extract.dct_decoder import DctDecoder
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.degenerator.de_shuffler import DeShuffler
+
+    frame = np.load(os.path.join(golden_dir, "frame63_crop.npz"))["bgr"]
+    for enc, dec, o_dec in ((DwtDctSvdEncoder(), DwtDctSvdDecoder(), o_svd.decode),
+                            (DctEncoder(), DctDecoder(), None)):
+        yuv = bracket.to_yuv(frame)
+        wm = Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(yuv.shape))
+        enc.read_wm(wm)
+        before = yuv.copy()
+        out = enc.encode(yuv)
+        assert out is yuv and not np.array_equal(yuv, before)
+        assert np.array_equal(yuv[:, :, 0], before[:, :, 0])
+        marked = bracket.from_yuv(yuv.copy())
+        decoded = dec.decode(bracket.to_yuv(marked))
+        assert isinstance(decoded, np.ndarray) and decoded.dtype == np.float64
+        assert decoded.shape == (1, frame.shape[0] * frame.shape[1] // 64)
+        ret = DeShuffler(key=KEY).set_shape(PAYLOAD.shape).degenerate(decoded)
+        assert ret.dtype == np.uint8 and np.array_equal(ret, PAYLOAD)
+        # a plain ndarray (no device side-car) goes through the same kernels
+        assert np.array_equal(DeShuffler(key=KEY).set_shape(PAYLOAD.shape).degenerate(np.array(decoded)), PAYLOAD)
+        if o_dec is not None:
+            assert np.array_equal(o_pay.degenerate(o_dec(bracket.to_yuv(marked)), 8, KEY), PAYLOAD)
+
+
+def test_grayscale_payload_roundtrip():
+    """tests/test.py combo 1:0 (GrayScale generator + DwtDctSvd coder) with a 21x21 image payload."""
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.extract.dwt_dct_svd_decoder import DwtDctSvdDecoder
+    from offmark_b200.generator.grayscale import GrayScale
+    from offmark_b200.degenerator.de_grayscale import DeGrayScale
+    from oracle import synth
+    img = (np.random.RandomState(4).rand(21, 21) > 0.5).astype(np.uint8) * 255
+    frame = synth.random_bgr(1080, 1920, 8)
+    yuv = bracket.to_yuv(frame)
+    enc = DwtDctSvdEncoder()
+    enc.read_wm(GrayScale(key=KEY).generate_wm(img, enc.wm_capacity(yuv.shape)))
+    enc.encode(yuv)
+    back = DeGrayScale(key=KEY).set_shape(img.shape).degenerate(DwtDctSvdDecoder().decode(yuv))
+    assert back.shape == img.shape and np.array_equal(back, img)
+
+
+def test_hls_pattern_collector_flow():
+    """tests/segment_mark_detect_hls.py: per-segment payload = 8-bit segment number (:42-55),
+    per-frame patterns, Counter mode and frequency (:126-155) - batched on the GPU."""
+    from b200wm import ops
+    from b200wm.vote import SegmentVote
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.extract.dwt_dct_svd_decoder import DwtDctSvdDecoder
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.degenerator.de_shuffler import DeShuffler
+    from oracle import synth
+    dev = torch.device("cuda:0")
+    S, F, h, w = 5, 12, 240, 320
+    planes = torch.from_numpy(np.stack([synth.luma_plane_u8(h, w, f, 31) for f in range(S * F)])).to(dev)
+    seg_ids = [3, 77, 130, 255, 256]
+    payloads = [o_pay.payload_for_segment(s) for s in seg_ids]
+    enc, dec = DwtDctSvdEncoder(), DwtDctSvdDecoder()
+    rows = np.stack([Shuffler(key=KEY).generate_wm(p, enc.wm_capacity((h, w, 3)))[0] for p in payloads])
+    frame_seg = torch.arange(S * F, device=dev, dtype=torch.int32) // F
+    enc.read_wm(rows[:1])
+    enc.encode_planes(planes, wm_rows=rows, frame_wm_row=frame_seg)
+    raw, counts = dec.decode_planes(planes, payload_len=8)
+    deg = DeShuffler(key=KEY).set_shape((8,))
+    patterns, packed = deg.degenerate_counts(counts, h * w // 64)
+    vote = SegmentVote(S, 8, dev).add(packed, frame_segment=frame_seg).combine()
+    for s, (pattern, freq, bit_votes, frames) in enumerate(vote.result()):
+        assert np.array_equal(pattern, payloads[s]) and freq == 1.0 and frames == F
+        assert bit_votes.tolist() == (payloads[s] * F).tolist()
+    # the same frames through the oracle's per-frame path
+    host = planes.cpu().numpy()
+    for f in (0, F + 1, 4 * F + 3):
+        bits = o_svd.extract_plane(host[f])
+        assert np.array_equal(o_pay.degenerate(bits, 8, KEY), patterns[f].cpu().numpy())

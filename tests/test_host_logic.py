@@ -1,0 +1,134 @@
+"""CPU: host-side logic of the drop-in (generators, sharding, vote combine incl. world_size 2 on gloo)."""
+import os
+import socket
+from collections import Counter
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import payload as o_pay
+from parity import PAYLOAD
+
+
+def test_shuffler_matches_oracle():
+    from offmark_b200.generator.shuffler import Shuffler
+    for key, length, cap in ((0, 8, (1, 32400)), (5, 8, (1, 1200)), (0, 5, (1, 97)), (11, 16, (1, 129600))):
+        p = np.random.RandomState(key + 1).randint(0, 2, length)
+        a = Shuffler(key=key).generate_wm(p, cap)
+        b = o_pay.generate_wm(p, cap, key)
+        assert a.shape == b.shape == cap and a.dtype == b.dtype and np.array_equal(a, b)
+    assert Shuffler.wm_type() == "bits"
+    wm = Shuffler(key=0).generate_wm(PAYLOAD, (1, 64))
+    assert np.array_equal(wm[0, :8], PAYLOAD[[6, 2, 1, 7, 3, 0, 5, 4]])
+
+
+def test_grayscale_matches_oracle():
+    from offmark_b200.generator.grayscale import GrayScale
+    img = np.random.RandomState(2).randint(0, 256, (21, 21)).astype(np.uint8)
+    a = GrayScale(key=0).generate_wm(img, (1, 32400))
+    assert np.array_equal(a, o_pay.generate_wm_grayscale(img, (1, 32400), 0))
+    assert GrayScale.wm_type() == "grayscale"
+    with pytest.warns(UserWarning):
+        GrayScale(key=0).generate_wm(img, (1, 100))
+
+
+def test_sharding():
+    from b200wm.sharding import frame_shard, segment_shard
+    for n in (0, 1, 7, 3000, 1024):
+        for world in (1, 2, 4, 8):
+            spans = [frame_shard(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert segment_shard(10, 1, 4) == [1, 5, 9]
+    assert sorted(sum((segment_shard(64, r, 8) for r in range(8)), [])) == list(range(64))
+
+
+def _fill_vote_state(vote, patterns_int, segments, orders):
+    """Host-side stand-in for b200wm_pattern_hist so the combine logic can run without a GPU."""
+    L = vote.payload_len
+    for p, s, o in zip(patterns_int, segments, orders):
+        vote.hist[s, p] += 1
+        vote.first_seen[s, p] = min(int(vote.first_seen[s, p]), int(o))
+        vote.seg_frames[s] += 1
+        for j in range(L):
+            vote.bit_votes[s, j] += (p >> (L - 1 - j)) & 1
+
+
+def _reference_vote(patterns_int, L):
+    strings = [format(p, f"0{L}b") for p in patterns_int]
+    best, count = Counter(strings).most_common(1)[0]
+    return [int(c) for c in best], count / len(strings)
+
+
+def test_segment_vote_result_matches_counter_incl_ties():
+    from b200wm.vote import SegmentVote
+    rng = np.random.RandomState(0)
+    L, S = 8, 5
+    vote = SegmentVote(S, L, "cpu")
+    per_seg = {}
+    for s in range(S - 1):
+        pats = rng.choice([0x65, 0x9A, 0x01], size=60 if s else 4, p=[0.4, 0.4, 0.2]).tolist()
+        if s == 0:
+            pats = [0x9A, 0x65, 0x65, 0x9A]          # exact tie: first seen (0x9A) must win
+        per_seg[s] = pats
+        _fill_vote_state(vote, pats, [s] * len(pats), range(len(pats)))
+    res = vote.result()
+    for s, pats in per_seg.items():
+        want_p, want_f = _reference_vote(pats, L)
+        assert res[s][0].tolist() == want_p and res[s][1] == want_f and res[s][3] == len(pats)
+        assert res[s][2].tolist() == [sum((p >> (L - 1 - j)) & 1 for p in pats) for j in range(L)]
+    assert res[S - 1][0] is None and res[S - 1][1] is None and res[S - 1][3] == 0
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _vote_worker(rank, world, port, L, all_patterns, out_q):
+    import sys
+    from conftest import ROOT, PKG      # noqa: F401  (sets sys.path in the child)
+    from b200wm.vote import SegmentVote, gathered_pattern_vote
+    from b200wm.sharding import frame_shard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = len(all_patterns)
+    a, b = frame_shard(n, rank, world)
+    mine = all_patterns[a:b]
+    vote = SegmentVote(1, L, "cpu")
+    _fill_vote_state(vote, mine, [0] * len(mine), range(a, b))
+    vote.combine()
+    pattern, freq, bit_votes, frames = vote.result()[0]
+    bits = torch.tensor([[(p >> (L - 1 - j)) & 1 for j in range(L)] for p in mine], dtype=torch.uint8).reshape(-1, L)
+    gp, gf = gathered_pattern_vote(bits, torch.arange(a, b))
+    out_q.put((rank, pattern.tolist(), freq, bit_votes.tolist(), frames, gp.tolist(), gf))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_vote_combine_world_size_2_gloo():
+    L = 8
+    # tie between 0x65 and 0x9A across the two ranks; 0x9A appears first globally (rank 0, frame 1)
+    patterns = [0x01, 0x9A, 0x65, 0x65, 0x9A, 0x65, 0x9A, 0x02]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vote_worker, args=(r, 2, port, L, patterns, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    want_p, want_f = _reference_vote(patterns, L)
+    assert want_p == [int(c) for c in format(0x9A, "08b")]
+    for rank, pattern, freq, bit_votes, frames, gp, gf in got:
+        assert pattern == want_p and freq == want_f and frames == len(patterns)
+        assert bit_votes == [sum((p >> (L - 1 - j)) & 1 for p in patterns) for j in range(L)]
+        assert gp == want_p and gf == want_f

@@ -1,0 +1,144 @@
+"""CPU: the oracle reproduces the reference's outputs stored in tests/golden (made by
+oracle/make_golden.py from the reference itself)."""
+import json
+import os
+
+import numpy as np
+
+from oracle import bracket, dct8, dwt_dct_svd as svd, haar, payload, synth
+from parity import PAYLOAD, KEY
+
+
+def _bits(packed, n):
+    return np.unpackbits(packed)[:n].astype(np.float64).reshape(1, -1)
+
+
+def test_haar_roundtrip_and_ll():
+    rng = np.random.RandomState(0)
+    x = rng.uniform(-100, 255, (64, 96)).astype(np.float32)
+    ll, (lh, hl, hh) = haar.dwt2_haar(x)
+    assert ll.dtype == np.float32 and ll.shape == (32, 48)
+    s = (x[0::2, 0::2] + x[0::2, 1::2]) + (x[1::2, 0::2] + x[1::2, 1::2])
+    np.testing.assert_allclose(ll, s / 2, rtol=3e-7, atol=1e-5)
+    np.testing.assert_allclose(haar.idwt2_haar((ll, (lh, hl, hh))), x, rtol=0, atol=2e-4)
+
+
+def test_dct_is_orthogonal_so_it_drops_out_of_the_svd_pair():
+    """sigma(dct(B)) == sigma(B): the reason the CUDA path skips the 4x4 DCT (svd4.cuh)."""
+    import cv2
+    rng = np.random.RandomState(1)
+    for _ in range(200):
+        b = rng.uniform(-50, 500, (4, 4)).astype(np.float32)
+        s_dct = np.linalg.svd(cv2.dct(b).astype(np.float64), compute_uv=False)
+        s_raw = np.linalg.svd(b.astype(np.float64), compute_uv=False)
+        np.testing.assert_allclose(s_dct, s_raw, rtol=1e-5, atol=1e-3)
+
+
+def test_frame63_crop_dwtsvd(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frame63_crop.npz"))
+    frame = g["bgr"]
+    wm = payload.generate_wm(PAYLOAD, svd.wm_capacity(frame.shape), KEY)
+    yuv = svd.encode(bracket.to_yuv(frame), wm)
+    h, w = g["dwtsvd_marked_f32_ch1_window"].shape
+    assert np.array_equal(yuv[:h, :w, 1], g["dwtsvd_marked_f32_ch1_window"])
+    marked = bracket.from_yuv(yuv.copy())
+    assert np.array_equal(marked.astype(np.int16) - frame, g["dwtsvd_marked_minus_src"])
+    n = int(g["dwtsvd_nbits"])
+    assert np.array_equal(svd.decode(bracket.to_yuv(frame)), _bits(g["dwtsvd_bits_clean"], n))
+    assert np.array_equal(svd.decode(yuv), _bits(g["dwtsvd_bits_marked_f32"], n))
+    assert np.array_equal(svd.decode(bracket.to_yuv(marked)), _bits(g["dwtsvd_bits_marked_u8"], n))
+    for name in ("clean", "marked_f32", "marked_u8"):
+        bits = _bits(g[f"dwtsvd_bits_{name}"], n)
+        assert np.array_equal(payload.degenerate(bits, len(PAYLOAD), KEY), g[f"dwtsvd_pattern_{name}"])
+    assert np.array_equal(g["dwtsvd_pattern_marked_u8"], PAYLOAD)
+
+
+def test_frame63_crop_dct8(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frame63_crop.npz"))
+    frame = g["bgr"]
+    wm = payload.generate_wm(PAYLOAD, svd.wm_capacity(frame.shape), KEY)
+    yuv = dct8.encode(bracket.to_yuv(frame), wm)
+    h, w = g["dct8_marked_f32_ch1_window"].shape
+    assert np.array_equal(yuv[:h, :w, 1], g["dct8_marked_f32_ch1_window"])
+    marked = bracket.from_yuv(yuv.copy())
+    assert np.array_equal(marked.astype(np.int16) - frame, g["dct8_marked_minus_src"])
+    n = int(g["dct8_nbits"])
+    assert np.array_equal(dct8.decode(yuv), _bits(g["dct8_bits_marked_f32"], n))
+    assert np.array_equal(dct8.decode(bracket.to_yuv(marked)), _bits(g["dct8_bits_marked_u8"], n))
+
+
+def test_in_mp4_frames(golden_dir):
+    g = np.load(os.path.join(golden_dir, "in_mp4_frames.npz"))
+    wm = g["wm"].astype(np.int64)
+    for i in g["picks"]:
+        frame = g[f"rgb_{i}"]
+        marked = bracket.mark_frame(frame, lambda y: svd.encode(y, wm))
+        assert np.array_equal(marked.astype(np.int16) - frame, g[f"marked_minus_src_{i}"])
+        bits = svd.decode(bracket.to_yuv(marked))
+        assert np.array_equal(bits, _bits(g[f"bits_{i}"], bits.size))
+        assert np.array_equal(payload.degenerate(bits, 8, KEY), g["patterns_all_frames"][i])
+    best, freq = payload.pattern_vote(list(g["patterns_all_frames"]))
+    assert np.array_equal(best, g["vote_pattern"]) and freq == float(g["vote_frequency"])
+    assert np.array_equal(best, PAYLOAD)
+
+
+def test_synthetic_sizes(golden_dir):
+    g = np.load(os.path.join(golden_dir, "synthetic_sizes.npz"))
+    for n, (h, w) in enumerate(g["sizes"]):
+        tag = f"{h}x{w}"
+        if f"dwtsvd_{tag}_bits_marked" not in g:
+            continue
+        frame = synth.random_bgr(int(h), int(w), seed=100 + n)
+        wm = payload.generate_wm(PAYLOAD, svd.wm_capacity(frame.shape), KEY)
+        yuv = svd.encode(bracket.to_yuv(frame), wm)
+        assert np.array_equal(yuv[:, :, 1], g[f"dwtsvd_{tag}_marked_ch1"])
+        assert np.array_equal(svd.decode(yuv).reshape(-1), g[f"dwtsvd_{tag}_bits_marked"])
+        assert np.array_equal(svd.decode(bracket.to_yuv(frame)).reshape(-1), g[f"dwtsvd_{tag}_bits_clean"])
+        yuv8 = dct8.encode(bracket.to_yuv(frame), wm)
+        assert np.array_equal(yuv8[:, :, 1], g[f"dct8_{tag}_marked_ch1"])
+        assert np.array_equal(dct8.decode(yuv8).reshape(-1), g[f"dct8_{tag}_bits_marked"])
+
+
+def test_per_block_form_equals_vectorised():
+    frame = synth.random_bgr(40, 56, seed=5)
+    wm = payload.generate_wm(PAYLOAD, svd.wm_capacity(frame.shape), KEY)
+    a = svd.encode(bracket.to_yuv(frame), wm)
+    b = svd.encode_per_block(bracket.to_yuv(frame), wm)
+    assert np.array_equal(a, b)
+    assert np.array_equal(svd.decode(a), svd.decode_per_block(b))
+
+
+def test_payload_side(golden_dir):
+    with open(os.path.join(golden_dir, "payload.json")) as f:
+        pay = json.load(f)
+    for k, perm in pay["permutations"].items():
+        length, key = (int(v) for v in k.split(":"))
+        assert payload.permutation(length, key).tolist() == perm
+    assert payload.permutation(8, 0).tolist() == [6, 2, 1, 7, 3, 0, 5, 4]
+    for case in pay["degenerate_cases"]:
+        # rebuild a bit array with exactly these per-position counts
+        length, n = case["length"], case["n"]
+        bits = np.zeros(n)
+        for i, c in enumerate(case["counts"]):
+            idx = np.arange(i, n, length)
+            bits[idx[:c]] = 1
+        assert payload.degenerate(bits.reshape(1, -1), length, case["key"]).tolist() == case["pattern"]
+    assert payload.payload_for_segment(5).tolist() == [0, 0, 0, 0, 0, 1, 0, 1]
+    assert payload.payload_for_segment_copy(3, 2).tolist() == [0, 0, 1, 1, 0, 0, 1, 0]
+    assert payload.segment_copy_from_pattern([0, 0, 1, 1, 0, 0, 1, 0]) == (3, 2)
+
+
+def test_pattern_vote_ties_and_empty():
+    a, b = np.array([0, 1]), np.array([1, 0])
+    best, freq = payload.pattern_vote([b, a, a, b])
+    assert best.tolist() == [1, 0] and freq == 0.5           # first seen wins the tie
+    assert payload.pattern_vote([]) == (None, None)
+
+
+def test_u8_plane_1080p(golden_dir):
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "u8plane_1080p.npz"))
+    y = synth.luma_plane_u8(1080, 1920, int(g["frame_index"]), int(g["seed"]))
+    assert hashlib.sha256(y.tobytes()).hexdigest() == str(g["src_sha256"])
+    bits = svd.extract_plane(y)
+    assert np.array_equal(bits, _bits(g["bits_clean"], bits.size))

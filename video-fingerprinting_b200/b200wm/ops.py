@@ -1,0 +1,261 @@
+"""Batched, device-resident entry points over the C ABI (torch tensors in, torch tensors out).
+
+PyTorch is plumbing here: it owns device memory and the current stream, and every
+function below hands raw pointers to libb200wm.so.  Nothing in this module computes
+on the CPU or with torch operators; without the library or a CUDA device it raises.
+
+Tensor conventions
+  planes      uint8 or float32 CUDA tensor, ``[N, H, W]`` / ``[H, W]`` (planar) or
+              ``[N, H, W, C]`` / ``[H, W, C]`` with ``channel=c`` (interleaved).  Any strides
+              are fine as long as they are positive; the fast path needs planar uint8 with
+              8-byte aligned rows.
+  packed bits int32 tensors holding little-endian uint32 bit words (bit c -> word c>>5, bit c&31).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, Plane
+
+_ESIZE = {torch.uint8: (1, _lib.U8), torch.float32: (4, _lib.F32)}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.B200wmError("no CUDA device: the b200wm kernels have no CPU fallback")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Empty tensors made by ``_empty`` still have a
+    backing allocation, so the library never sees NULL for a required buffer."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr() if t.numel() else t.untyped_storage().data_ptr())
+
+
+def _empty(shape, dtype, device):
+    """torch.empty that keeps a non-NULL pointer even when a dimension is zero."""
+    n = 1
+    for d in shape:
+        n *= d
+    if n > 0:
+        return torch.empty(shape, dtype=dtype, device=device)
+    return torch.empty((1,), dtype=dtype, device=device)[:0].reshape(shape)
+
+
+def _as_nhw(t, channel):
+    """View ``t`` as [N, H, W] (no copy)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError("expected a CUDA tensor")
+    if t.dtype not in _ESIZE:
+        raise ValueError(f"unsupported dtype {t.dtype}: uint8 or float32 expected")
+    if channel is not None:
+        if t.dim() not in (3, 4):
+            raise ValueError("interleaved frames must be [H, W, C] or [N, H, W, C]")
+        t = t[..., channel]
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3:
+        raise ValueError("planes must be [H, W] or [N, H, W] (or interleaved with channel=...)")
+    return t
+
+
+def describe(t, channel=None):
+    """(view, b200wm_plane) for a tensor of planes."""
+    v = _as_nhw(t, channel)
+    esize, code = _ESIZE[v.dtype]
+    n, h, w = v.shape
+    sn, sh, sw = v.stride()
+    if n == 1:
+        sn = 0
+    if min(sh, sw) <= 0 or sn < 0:
+        raise ValueError("planes need positive strides")
+    return v, Plane(code, n, h, w, sh * esize, sn * esize, sw, 0)
+
+
+def geometry(height, width):
+    """(block_num, tile_count, words_per_frame) - the reference's capacity rules."""
+    return (int(lib.b200wm_block_num(height, width)), int(lib.b200wm_tile_count(height, width)),
+            int(lib.b200wm_words_per_frame(height, width)))
+
+
+# ----------------------------------------------------------------------------- bit packing
+def pack_bits(bits, device=None):
+    """0/1 array ``[rows, n]`` or ``[n]`` -> (int32 tensor [rows, words], n).  Host-side, tiny."""
+    a = np.asarray(bits)
+    if a.ndim == 1:
+        a = a[None, :]
+    if a.ndim != 2:
+        raise ValueError("bits must be 1-D or 2-D")
+    if a.size and not np.isin(a, (0, 1)).all():
+        raise ValueError("watermark bits must be 0 or 1")
+    rows, n = a.shape
+    words = max(1, (n + 31) // 32)
+    packed = np.zeros((rows, words * 4), dtype=np.uint8)
+    if n:
+        pb = np.packbits(a.astype(np.uint8), axis=1, bitorder="little")
+        packed[:, :pb.shape[1]] = pb
+    t = torch.from_numpy(packed.view("<i4").copy())
+    return (t.to(device) if device is not None else t), n
+
+
+def unpack_bits(raw_bits, n):
+    """int32 tensor [N, words] -> numpy uint8 [N, n] (host)."""
+    a = raw_bits.detach().cpu().numpy().view(np.uint8)
+    return np.unpackbits(a, axis=1, bitorder="little")[:, :n]
+
+
+# ----------------------------------------------------------------------------- DWT / SVD pair
+def dwtsvd_embed_(planes, wm_packed, wm_len, scale=15.0, channel=None, frame_wm_row=None, out=None):
+    """In-place (or into ``out``, same geometry, pre-filled) embed.  Returns the written tensor."""
+    require_cuda()
+    v, pl = describe(planes, channel)
+    dst_t = planes if out is None else out
+    dv, dpl = describe(dst_t, channel)
+    if (dpl.pitch_bytes, dpl.frame_stride_bytes, dpl.elem_stride, dpl.height, dpl.width, dpl.n_frames, dpl.dtype) != \
+            (pl.pitch_bytes, pl.frame_stride_bytes, pl.elem_stride, pl.height, pl.width, pl.n_frames, pl.dtype):
+        raise ValueError("out must have the geometry of planes")
+    if wm_packed.dtype != torch.int32 or wm_packed.dim() != 2 or not wm_packed.is_contiguous() or not wm_packed.is_cuda:
+        raise ValueError("wm_packed must be a contiguous CUDA int32 [rows, words] tensor (see pack_bits)")
+    if frame_wm_row is not None and (frame_wm_row.dtype != torch.int32 or frame_wm_row.numel() != pl.n_frames
+                                     or not frame_wm_row.is_cuda or not frame_wm_row.is_contiguous()):
+        raise ValueError("frame_wm_row must be a contiguous CUDA int32 [n_frames] tensor")
+    check(lib.b200wm_dwtsvd_embed(_ptr(v), _ptr(dv), C.byref(pl), _ptr(wm_packed), wm_packed.shape[1], int(wm_len),
+                                  _ptr(frame_wm_row), float(scale), _stream()))
+    return dst_t
+
+
+def dwtsvd_extract(planes, scale=15.0, payload_len=None, channel=None, raw_bits=None, pos_counts=None):
+    """-> (raw_bits int32 [N, words], pos_counts int32 [N, payload_len] or None)."""
+    require_cuda()
+    v, pl = describe(planes, channel)
+    _, _, words = geometry(pl.height, pl.width)
+    if raw_bits is None:
+        raw_bits = _empty((pl.n_frames, words), torch.int32, v.device)
+    if payload_len is not None and pos_counts is None:
+        pos_counts = torch.empty((pl.n_frames, payload_len), dtype=torch.int32, device=v.device)
+    check(lib.b200wm_dwtsvd_extract(_ptr(v), C.byref(pl), float(scale), _ptr(raw_bits),
+                                    words, int(payload_len or 0), _ptr(pos_counts), _stream()))
+    return raw_bits, pos_counts
+
+
+def dwtsvd_sigma(planes, channel=None):
+    """sigma_0 of every walked block, float32 [N, tiles] (validation aid)."""
+    require_cuda()
+    v, pl = describe(planes, channel)
+    _, tiles, _ = geometry(pl.height, pl.width)
+    sigma = _empty((pl.n_frames, tiles), torch.float32, v.device)
+    check(lib.b200wm_dwtsvd_sigma(_ptr(v), C.byref(pl), _ptr(sigma), _stream()))
+    return sigma
+
+
+# ----------------------------------------------------------------------------- 8x8 DCT pair
+def dct8_masks(lum, channel=None):
+    """-> (block_mean f32 [N, nb], tex_mask f32 [N, nb], frame_sum f64 [N])."""
+    require_cuda()
+    v, pl = describe(lum, channel)
+    nb = (pl.height // 8) * (pl.width // 8)
+    block_mean = _empty((pl.n_frames, nb), torch.float32, v.device)
+    tex = _empty((pl.n_frames, nb), torch.float32, v.device)
+    frame_sum = _empty((pl.n_frames,), torch.float64, v.device)
+    check(lib.b200wm_dct8_masks(_ptr(v), C.byref(pl), _ptr(block_mean), _ptr(tex), _ptr(frame_sum), _stream()))
+    return block_mean, tex, frame_sum
+
+
+def dct8_embed_(planes, masks, wm_packed, wm_len, alpha=20.0, channel=None, frame_wm_row=None):
+    require_cuda()
+    v, pl = describe(planes, channel)
+    block_mean, tex, frame_sum = masks
+    check(lib.b200wm_dct8_embed(_ptr(v), _ptr(v), C.byref(pl), _ptr(block_mean), _ptr(tex), _ptr(frame_sum),
+                                _ptr(wm_packed), wm_packed.shape[1], int(wm_len), _ptr(frame_wm_row),
+                                float(alpha), _stream()))
+    return planes
+
+
+def dct8_extract(planes, masks, alpha=20.0, payload_len=None, channel=None):
+    require_cuda()
+    v, pl = describe(planes, channel)
+    block_mean, tex, frame_sum = masks
+    _, _, words = geometry(pl.height, pl.width)
+    raw_bits = _empty((pl.n_frames, words), torch.int32, v.device)
+    pos_counts = None
+    if payload_len is not None:
+        pos_counts = torch.empty((pl.n_frames, payload_len), dtype=torch.int32, device=v.device)
+    check(lib.b200wm_dct8_extract(_ptr(v), C.byref(pl), _ptr(block_mean), _ptr(tex), _ptr(frame_sum), float(alpha),
+                                  _ptr(raw_bits), words, int(payload_len or 0), _ptr(pos_counts), _stream()))
+    return raw_bits, pos_counts
+
+
+# ----------------------------------------------------------------------------- votes
+def vote_counts(raw_bits, block_num, payload_len):
+    require_cuda()
+    n, words = raw_bits.shape
+    counts = torch.empty((n, payload_len), dtype=torch.int32, device=raw_bits.device)
+    check(lib.b200wm_vote_counts(_ptr(raw_bits), n, words, int(block_num), int(payload_len), _ptr(counts), _stream()))
+    return counts
+
+
+def vote_finish(pos_counts, block_num, perm):
+    """Per-frame finish of DeShuffler.degenerate -> (patterns uint8 [N, L], packed int64 [N] or None)."""
+    require_cuda()
+    n, length = pos_counts.shape
+    if perm.dtype != torch.int32 or perm.numel() != length or not perm.is_cuda:
+        raise ValueError("perm must be a CUDA int32 tensor of payload_len entries")
+    patterns = torch.empty((n, length), dtype=torch.uint8, device=pos_counts.device)
+    packed = torch.empty((n,), dtype=torch.int64, device=pos_counts.device) if length <= 64 else None
+    check(lib.b200wm_vote_finish(_ptr(pos_counts), n, length, int(block_num), _ptr(perm), _ptr(patterns), _ptr(packed),
+                                 _stream()))
+    return patterns, packed
+
+
+INT32_MAX = 2 ** 31 - 1
+
+
+def pattern_hist(packed, payload_len, n_segments=1, frame_segment=None, frame_order=None, order_offset=0, state=None):
+    """Accumulate the device half of the cross-frame vote.  ``state`` (from a previous call) is
+    updated in place.  -> dict(hist, first_seen, bit_votes, seg_frames)."""
+    require_cuda()
+    dev = packed.device
+    if state is None:
+        state = {
+            "hist": torch.zeros((n_segments, 1 << payload_len), dtype=torch.int32, device=dev),
+            "first_seen": torch.full((n_segments, 1 << payload_len), INT32_MAX, dtype=torch.int32, device=dev),
+            "bit_votes": torch.zeros((n_segments, payload_len), dtype=torch.int32, device=dev),
+            "seg_frames": torch.zeros((n_segments,), dtype=torch.int32, device=dev),
+        }
+    check(lib.b200wm_pattern_hist(_ptr(packed), _ptr(frame_segment), _ptr(frame_order), int(order_offset),
+                                  packed.numel(), int(payload_len), int(n_segments), _ptr(state["hist"]),
+                                  _ptr(state["first_seen"]), _ptr(state["bit_votes"]), _ptr(state["seg_frames"]),
+                                  _stream()))
+    return state
+
+
+# ----------------------------------------------------------------------------- colour bracket
+def bgr8_to_yuv32(frames):
+    """uint8 [..., 3] contiguous -> float32 same shape (video/embedder.py:34)."""
+    require_cuda()
+    if frames.dtype != torch.uint8 or not frames.is_contiguous() or frames.shape[-1] != 3:
+        raise ValueError("frames must be contiguous uint8 [..., 3]")
+    out = torch.empty(frames.shape, dtype=torch.float32, device=frames.device)
+    check(lib.b200wm_bgr8_to_yuv32(_ptr(frames), _ptr(out), frames.numel() // 3, _stream()))
+    return out
+
+
+def yuv32_to_bgr8(yuv):
+    """float32 [..., 3] contiguous -> uint8 with clip / round-half-even (video/embedder.py:36-38)."""
+    require_cuda()
+    if yuv.dtype != torch.float32 or not yuv.is_contiguous() or yuv.shape[-1] != 3:
+        raise ValueError("yuv must be contiguous float32 [..., 3]")
+    out = torch.empty(yuv.shape, dtype=torch.uint8, device=yuv.device)
+    check(lib.b200wm_yuv32_to_bgr8(_ptr(yuv), _ptr(out), yuv.numel() // 3, _stream()))
+    return out
+
+
+def kernel_launches():
+    return int(lib.b200wm_kernel_launches())

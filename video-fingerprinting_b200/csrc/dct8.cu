@@ -1,0 +1,363 @@
+// 8x8 block-DCT quantisation-index pair: perceptual masks, embed, extract (sm_100a).
+//
+// Replaces the three per-block Python loops of the reference:
+//   masks   src/offmark/embed/dct_encoder.py:41-102 (verbatim duplicate at extract/dct_decoder.py:29-89)
+//   embed   src/offmark/embed/dct_encoder.py:24-38
+//   extract src/offmark/extract/dct_decoder.py:17-27
+//
+// One thread owns one 8x8 block, all 64 samples in registers.  The luminance block goes through
+// a full 2-D DCT-II (orthonormal, like cv2.dct) built from 16 register-resident 8-point
+// even/odd butterflies, because the texture mask needs every coefficient.  The chroma block
+// only ever has coefficient [2][1] changed, so embed/extract project onto that one basis
+// function (72 FMA) and the embed adds delta * basis back (the rest of cv2.dct -> cv2.idct
+// is the identity up to float32 rounding).
+//
+// The luminance mask depends on the frame-wide mean of the block means (dct_encoder.py:54-56),
+// so masks are a separate pass that also accumulates that sum per frame; embed/extract read
+// the per-block mean, texture mask and the frame sum (12 bytes per 64 samples).
+#include "common.cuh"
+
+namespace b200wm {
+
+constexpr int kDctThreads = 128;
+
+// cos(k*pi/16), and the orthonormal scale factors
+#define C1 0.98078528040323043f
+#define C2 0.92387953251128674f
+#define C3 0.83146961230254524f
+#define C4 0.70710678118654752f
+#define C5 0.55557023301960218f
+#define C6 0.38268343236508977f
+#define C7 0.19509032201612825f
+
+// Orthonormal 8-point DCT-II in place: X_k = a_k sum_n x_n cos((2n+1) k pi / 16), a_0 = 1/sqrt(8), a_k = 1/2.
+__device__ __forceinline__ void dct8_1d(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
+                                        float& x7) {
+    const float s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
+    const float d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
+    const float e0 = s0 + s3, e1 = s1 + s2, e2 = s1 - s2, e3 = s0 - s3;
+    x0 = (e0 + e1) * (0.5f * C4);
+    x4 = (e0 - e1) * (0.5f * C4);
+    x2 = fmaf(e3, 0.5f * C2, e2 * (0.5f * C6));
+    x6 = fmaf(e3, 0.5f * C6, e2 * (-0.5f * C2));
+    x1 = fmaf(d3, 0.5f * C7, fmaf(d2, 0.5f * C5, fmaf(d1, 0.5f * C3, d0 * (0.5f * C1))));
+    x3 = fmaf(d3, -0.5f * C5, fmaf(d2, -0.5f * C1, fmaf(d1, -0.5f * C7, d0 * (0.5f * C3))));
+    x5 = fmaf(d3, 0.5f * C3, fmaf(d2, 0.5f * C7, fmaf(d1, -0.5f * C1, d0 * (0.5f * C5))));
+    x7 = fmaf(d3, -0.5f * C1, fmaf(d2, 0.5f * C3, fmaf(d1, -0.5f * C5, d0 * (0.5f * C7))));
+}
+
+template <typename T>
+__device__ __forceinline__ void load_block(const uint8_t* p, long long pitch, int es, float (&b)[64]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        const T* r = reinterpret_cast<const T*>(p + y * pitch);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) b[8 * y + x] = (float)r[x * es];
+    }
+}
+
+struct BlockGeom {
+    int bx, by, nb;                 // 8x8 blocks per row / column / frame
+    unsigned long long div_magic;   // c / bx == (c * magic) >> 40
+};
+
+static BlockGeom make_block_geom(int height, int width) {
+    BlockGeom g;
+    g.bx = width / 8;
+    g.by = height / 8;
+    g.nb = g.bx * g.by;
+    g.div_magic = g.bx > 0 ? ((1ull << 40) / (unsigned long long)g.bx + 1ull) : 0ull;
+    return g;
+}
+
+struct DctPlane {
+    const uint8_t* src;
+    uint8_t* dst;
+    long long pitch, frame_stride;
+    int elem_stride, is_f32;
+};
+
+// ---- masks -------------------------------------------------------------------------------------
+// texture_mask (dct_encoder.py:70-102).  Sums are float32, accumulated in the order the Python
+// expressions and numpy's 8-lane pairwise float32 sum use.
+__device__ __forceinline__ float texture_mask(const float (&c)[64]) {
+    float a[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) a[k] = fabsf(c[k]);
+    const float dcl = ((((a[0] + a[1]) + a[2]) + a[8]) + a[9]) + a[16];
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+#pragma unroll
+    for (int i = 1; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += a[8 * i + j];
+    const float total = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    const float eh = total - dcl;
+    float mask = 1.0f;
+    if (eh > 125.0f) {
+        const float e = ((((((((((a[24] + a[32]) + a[40]) + a[48]) + a[3]) + a[4]) + a[5]) + a[6]) + a[17]) + a[10]) +
+                         a[18]) + a[27];
+        const float h = eh - e;
+        const float l = dcl - a[0];
+        const float l_e = l / e, le_h = (l + e) / h;
+        const float ramp = 1.0f + (1.25f * (eh - 290.0f)) / 1510.0f;
+        const float strong = (l + e <= 400.0f) ? 1.125f : 1.25f;
+        if (eh > 900.0f) {
+            const bool rule = (l_e >= 1.4f && le_h >= 1.1f) || (l_e >= 1.1f && le_h >= 1.4f) || le_h > 4.0f;
+            mask = rule ? strong : ramp;
+        } else {
+            const bool rule = (l_e >= 2.3f && le_h >= 1.6f) || (l_e >= 1.6f && le_h >= 2.3f) || le_h > 4.0f;
+            mask = rule ? strong : ((e + h > 290.0f) ? ramp : 1.0f);
+        }
+    }
+    return mask;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kDctThreads) dct8_masks_kernel(DctPlane pl, BlockGeom g, float* __restrict__ block_mean,
+                                                                 float* __restrict__ tex_mask,
+                                                                 double* __restrict__ frame_sum, int frame0) {
+    const int frame = frame0 + blockIdx.y;
+    const unsigned c = blockIdx.x * kDctThreads + threadIdx.x;
+    double mean_d = 0.0;
+    if (c < (unsigned)g.nb) {
+        const unsigned by = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
+        const unsigned bx = c - by * g.bx;
+        const uint8_t* p = pl.src + frame * pl.frame_stride + (long long)(by * 8) * pl.pitch +
+                           (long long)bx * 8 * pl.elem_stride * (long long)sizeof(T);
+        float b[64];
+        load_block<T>(p, pl.pitch, pl.elem_stride, b);
+#pragma unroll
+        for (int y = 0; y < 8; ++y)
+            dct8_1d(b[8 * y], b[8 * y + 1], b[8 * y + 2], b[8 * y + 3], b[8 * y + 4], b[8 * y + 5], b[8 * y + 6], b[8 * y + 7]);
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+            dct8_1d(b[x], b[8 + x], b[16 + x], b[24 + x], b[32 + x], b[40 + x], b[48 + x], b[56 + x]);
+        const float mean = b[0] * 0.125f;                  // mask[i][j] = coeffs[0][0]; mask /= 8
+        const long long o = (long long)frame * g.nb + c;
+        block_mean[o] = mean;
+        tex_mask[o] = texture_mask(b);
+        mean_d = (double)mean;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mean_d += __shfl_xor_sync(0xFFFFFFFFu, mean_d, s);
+    if ((threadIdx.x & 31) == 0 && mean_d != 0.0) atomicAdd(&frame_sum[frame], mean_d);
+}
+
+// luminance_mask (dct_encoder.py:52-67) for one block, in float64 like the reference.
+__device__ __forceinline__ double luminance_mask(double m, double frame_sum, int nb) {
+    const double l_min = 90.0, l_max = 255.0, f_max = 2.0;
+    const double avg = frame_sum / (double)nb;
+    const double mean = avg > l_min ? avg : l_min;
+    const double f_ref = 1.0 + (mean - l_min) * (f_max - 1.0) / (l_max - l_min);
+    if (m > mean) return 1.0 + (m - mean) / (l_max - mean) * (f_max - f_ref);
+    if (m < 15.0) return 1.25;
+    if (m < 25.0) return 1.125;
+    return 1.0;
+}
+
+// basis of coefficient [2][1]: b2[y] * b1[x]
+__device__ __forceinline__ void basis21(float (&b1)[8], float (&b2)[8]) {
+    b1[0] = 0.5f * C1; b1[1] = 0.5f * C3; b1[2] = 0.5f * C5; b1[3] = 0.5f * C7;
+    b1[4] = -0.5f * C7; b1[5] = -0.5f * C5; b1[6] = -0.5f * C3; b1[7] = -0.5f * C1;
+    b2[0] = 0.5f * C2; b2[1] = 0.5f * C6; b2[2] = -0.5f * C6; b2[3] = -0.5f * C2;
+    b2[4] = -0.5f * C2; b2[5] = -0.5f * C6; b2[6] = 0.5f * C6; b2[7] = 0.5f * C2;
+}
+
+__device__ __forceinline__ float project21(const float (&b)[64], const float (&b1)[8], const float (&b2)[8]) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        float h = b[8 * y] * b1[0];
+#pragma unroll
+        for (int x = 1; x < 8; ++x) h = fmaf(b[8 * y + x], b1[x], h);
+        acc = fmaf(h, b2[y], acc);
+    }
+    return acc;
+}
+
+struct DctWm {
+    const uint32_t* wm;
+    const int32_t* frame_row;
+    int wm_words;
+    double alpha;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kDctThreads) dct8_embed_kernel(DctPlane pl, BlockGeom g, const float* __restrict__ block_mean,
+                                                                 const float* __restrict__ tex_mask,
+                                                                 const double* __restrict__ frame_sum, DctWm wm, int frame0) {
+    const int frame = frame0 + blockIdx.y;
+    const unsigned c = blockIdx.x * kDctThreads + threadIdx.x;
+    if (c >= (unsigned)g.nb) return;
+    const unsigned by = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
+    const unsigned bx = c - by * g.bx;
+    const long long boff = frame * pl.frame_stride + (long long)(by * 8) * pl.pitch +
+                           (long long)bx * 8 * pl.elem_stride * (long long)sizeof(T);
+    float b[64], b1[8], b2[8];
+    load_block<T>(pl.src + boff, pl.pitch, pl.elem_stride, b);
+    basis21(b1, b2);
+    const float c21 = project21(b, b1, b2);
+
+    const long long o = (long long)frame * g.nb + c;
+    const double mask = (double)tex_mask[o] * luminance_mask((double)block_mean[o], frame_sum[frame], g.nb);
+    const double step = wm.alpha * mask, step2 = step + step;
+    const int row = wm.frame_row ? wm.frame_row[frame] : 0;
+    const int bit = (wm.wm[(long long)row * wm.wm_words + (c >> 5)] >> (c & 31)) & 1;
+    // coeffs[2][1] = sign(c) * (floor(|c| / step2) * step2 [+ step]); np.sign(0) == 0 (dct_encoder.py:33,35)
+    double base = floor(fabs((double)c21) / step2) * step2;
+    if (bit) base += step;
+    const double sgn = c21 > 0.0f ? 1.0 : (c21 < 0.0f ? -1.0 : 0.0);
+    const float c21_new = (float)(sgn * base);
+    const float delta = c21_new - c21;
+
+    uint8_t* op = pl.dst + boff;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        T* orow = reinterpret_cast<T*>(op + y * pl.pitch);
+        const float dy = delta * b2[y];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const float f = fmaf(dy, b1[x], b[8 * y + x]);
+            if (sizeof(T) == 1) orow[x * pl.elem_stride] = (T)__float2int_rn(fminf(fmaxf(f, 0.0f), 255.0f));
+            else orow[x * pl.elem_stride] = (T)f;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kDctThreads) dct8_extract_kernel(DctPlane pl, BlockGeom g, const float* __restrict__ block_mean,
+                                                                   const float* __restrict__ tex_mask,
+                                                                   const double* __restrict__ frame_sum, double alpha,
+                                                                   uint32_t* __restrict__ raw_bits, int words,
+                                                                   int32_t* pos_counts, int L, int frame0) {
+    const int frame = frame0 + blockIdx.y;
+    const unsigned c = blockIdx.x * kDctThreads + threadIdx.x;
+    const unsigned word = c >> 5;
+    const bool live = word < (unsigned)words;
+    int bit = 0;
+    if (c < (unsigned)g.nb) {
+        const unsigned by = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
+        const unsigned bx = c - by * g.bx;
+        const long long boff = frame * pl.frame_stride + (long long)(by * 8) * pl.pitch +
+                               (long long)bx * 8 * pl.elem_stride * (long long)sizeof(T);
+        float b[64], b1[8], b2[8];
+        load_block<T>(pl.src + boff, pl.pitch, pl.elem_stride, b);
+        basis21(b1, b2);
+        const float c21 = project21(b, b1, b2);
+        const long long o = (long long)frame * g.nb + c;
+        const double mask = (double)tex_mask[o] * luminance_mask((double)block_mean[o], frame_sum[frame], g.nb);
+        const double step = alpha * mask;
+        // int(np.around(c21 / step) % 2 == 1): around is round-half-even, % is Python's (dct_decoder.py:24)
+        const double v = rint((double)c21 / step);
+        bit = fmod(fabs(v), 2.0) == 1.0 ? 1 : 0;
+    }
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
+    const unsigned lane = threadIdx.x & 31;
+    if (lane == 0 && live) raw_bits[(long long)frame * words + word] = ballot;
+    if (pos_counts) {
+        __shared__ int cta_counts[32];
+        if (threadIdx.x < 32) cta_counts[threadIdx.x] = 0;
+        __syncthreads();
+        if ((int)lane < L) {
+            const unsigned every = L == 32 ? 1u : (0xFFFFFFFFu / ((1u << L) - 1u));
+            const int n = __popc(ballot & (every << lane));
+            if (n) atomicAdd(&cta_counts[lane], n);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < L && cta_counts[threadIdx.x])
+            atomicAdd(&pos_counts[(long long)frame * L + threadIdx.x], cta_counts[threadIdx.x]);
+    }
+}
+
+// ---- launchers --------------------------------------------------------------------------------------
+int validate_plane(const b200wm_plane* pl);
+int launch_vote_counts(const uint32_t* raw_bits, int n_frames, int words_per_frame, long long block_num,
+                       int payload_len, int32_t* pos_counts, cudaStream_t stream);
+
+static DctPlane make_dct_plane(const void* src, void* dst, const b200wm_plane* pl) {
+    return DctPlane{(const uint8_t*)src, (uint8_t*)dst, pl->pitch_bytes, pl->frame_stride_bytes, pl->elem_stride,
+                    pl->dtype == B200WM_F32};
+}
+
+#define FOR_FRAME_CHUNKS(n_frames, gx, ...)                                                          \
+    for (int f0 = 0; f0 < (n_frames); f0 += 65535) {                                                 \
+        const dim3 grid((gx), (unsigned)(((n_frames)-f0) < 65535 ? ((n_frames)-f0) : 65535));         \
+        __VA_ARGS__;                                                                                 \
+    }
+
+int launch_dct8_masks(const void* lum, const b200wm_plane* pl, float* block_mean, float* tex_mask, double* frame_sum,
+                      cudaStream_t stream) {
+    int rc = validate_plane(pl);
+    if (rc) return rc;
+    if (!lum || !block_mean || !tex_mask || !frame_sum) return B200WM_ERR_INVALID;
+    if (pl->n_frames == 0) return B200WM_OK;
+    B200WM_CUDA_TRY(cudaMemsetAsync(frame_sum, 0, sizeof(double) * (size_t)pl->n_frames, stream));
+    const BlockGeom g = make_block_geom(pl->height, pl->width);
+    if (g.nb == 0) return B200WM_OK;
+    const DctPlane dp = make_dct_plane(lum, nullptr, pl);
+    const unsigned gx = (g.nb + kDctThreads - 1) / kDctThreads;
+    FOR_FRAME_CHUNKS(pl->n_frames, gx, {
+        if (dp.is_f32) dct8_masks_kernel<float><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, f0);
+        else dct8_masks_kernel<uint8_t><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, f0);
+        B200WM_LAUNCH_CHECK("dct8_masks_kernel");
+    })
+    return B200WM_OK;
+}
+
+int launch_dct8_embed(const void* src, void* dst, const b200wm_plane* pl, const float* block_mean, const float* tex_mask,
+                      const double* frame_sum, const uint32_t* wm, int wm_words, long long wm_len,
+                      const int32_t* frame_row, float alpha, cudaStream_t stream) {
+    int rc = validate_plane(pl);
+    if (rc) return rc;
+    if (!src || !dst || !block_mean || !tex_mask || !frame_sum || !wm || wm_words <= 0 || !(alpha > 0.0f))
+        return B200WM_ERR_INVALID;
+    const BlockGeom g = make_block_geom(pl->height, pl->width);
+    if (wm_len < g.nb || (long long)wm_words * 32 < g.nb) return B200WM_ERR_SHORT_WM;
+    if (g.nb == 0 || pl->n_frames == 0) return B200WM_OK;
+    const DctPlane dp = make_dct_plane(src, dst, pl);
+    const DctWm w{wm, frame_row, wm_words, (double)alpha};
+    const unsigned gx = (g.nb + kDctThreads - 1) / kDctThreads;
+    FOR_FRAME_CHUNKS(pl->n_frames, gx, {
+        if (dp.is_f32) dct8_embed_kernel<float><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, w, f0);
+        else dct8_embed_kernel<uint8_t><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, w, f0);
+        B200WM_LAUNCH_CHECK("dct8_embed_kernel");
+    })
+    return B200WM_OK;
+}
+
+int launch_dct8_extract(const void* src, const b200wm_plane* pl, const float* block_mean, const float* tex_mask,
+                        const double* frame_sum, float alpha, uint32_t* raw_bits, int words_per_frame, int payload_len,
+                        int32_t* pos_counts, cudaStream_t stream) {
+    int rc = validate_plane(pl);
+    if (rc) return rc;
+    if (!src || !block_mean || !tex_mask || !frame_sum || !raw_bits || !(alpha > 0.0f)) return B200WM_ERR_INVALID;
+    if (pos_counts && payload_len <= 0) return B200WM_ERR_INVALID;
+    const TileGeom tg = make_geom(pl->height, pl->width);     // block_num and words are the same formulas
+    if (words_per_frame != tg.words) return B200WM_ERR_INVALID;
+    if (pl->n_frames == 0) return B200WM_OK;
+    const BlockGeom g = make_block_geom(pl->height, pl->width);
+    const bool fused = pos_counts && payload_len <= 32 && (32 % payload_len) == 0;
+    if (fused)
+        B200WM_CUDA_TRY(cudaMemsetAsync(pos_counts, 0, sizeof(int32_t) * (size_t)pl->n_frames * payload_len, stream));
+    if (tg.words > 0) {
+        const DctPlane dp = make_dct_plane(src, nullptr, pl);
+        const unsigned gx = ((unsigned)tg.words * 32 + kDctThreads - 1) / kDctThreads;
+        int32_t* pc = fused ? pos_counts : nullptr;
+        FOR_FRAME_CHUNKS(pl->n_frames, gx, {
+            if (dp.is_f32)
+                dct8_extract_kernel<float><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, (double)alpha,
+                                                                            raw_bits, tg.words, pc, payload_len, f0);
+            else
+                dct8_extract_kernel<uint8_t><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, (double)alpha,
+                                                                              raw_bits, tg.words, pc, payload_len, f0);
+            B200WM_LAUNCH_CHECK("dct8_extract_kernel");
+        })
+    }
+    if (pos_counts && !fused)
+        return launch_vote_counts(raw_bits, pl->n_frames, words_per_frame, tg.block_num, payload_len, pos_counts, stream);
+    return B200WM_OK;
+}
+
+}  // namespace b200wm

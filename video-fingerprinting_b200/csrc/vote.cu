@@ -1,0 +1,166 @@
+// Vote kernels: per-position counts, the per-frame finish of DeShuffler.degenerate, and the
+// device half of the cross-frame pattern vote.
+//
+//   counts / finish  src/offmark/degenerator/de_shuffler.py:14-22
+//   pattern vote     tests/segment_mark_detect_hls.py:144-155 (Counter.most_common)
+#include "common.cuh"
+#include <limits.h>
+
+namespace b200wm {
+
+// ---- general per-position counts from packed raw bits (any payload_len) ---------------------
+// grid = (chunks, frames); each thread walks words with a stride; set bits are added to a
+// shared-memory histogram (payload_len <= kSmemPositions) or straight to global memory.
+constexpr int kSmemPositions = 8192;
+
+__global__ void __launch_bounds__(256) vote_counts_kernel(const uint32_t* __restrict__ raw_bits, int words,
+                                                          long long block_num, int L, int32_t* __restrict__ counts,
+                                                          int frame0) {
+    extern __shared__ int smem_counts[];
+    const int frame = frame0 + blockIdx.y;
+    const bool use_smem = L <= kSmemPositions;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < L; i += blockDim.x) smem_counts[i] = 0;
+        __syncthreads();
+    }
+    int32_t* out = counts + (long long)frame * L;
+    const uint32_t* bits = raw_bits + (long long)frame * words;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+        uint32_t m = bits[w];
+        const long long base = (long long)w * 32;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const long long c = base + b;
+            if (c < block_num) {
+                const int pos = (int)(c % L);
+                if (use_smem) atomicAdd(&smem_counts[pos], 1);
+                else atomicAdd(&out[pos], 1);
+            }
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += blockDim.x)
+            if (smem_counts[i]) atomicAdd(&out[i], smem_counts[i]);
+    }
+}
+
+int launch_vote_counts(const uint32_t* raw_bits, int n_frames, int words_per_frame, long long block_num,
+                       int payload_len, int32_t* pos_counts, cudaStream_t stream) {
+    if (!raw_bits || !pos_counts || n_frames < 0 || words_per_frame < 0 || payload_len <= 0 || block_num < 0)
+        return B200WM_ERR_INVALID;
+    if ((long long)words_per_frame * 32 < block_num) return B200WM_ERR_INVALID;
+    if (n_frames == 0) return B200WM_OK;
+    B200WM_CUDA_TRY(cudaMemsetAsync(pos_counts, 0, sizeof(int32_t) * (size_t)n_frames * payload_len, stream));
+    if (words_per_frame == 0) return B200WM_OK;
+    const int threads = 256;
+    int chunks = (words_per_frame + threads * 4 - 1) / (threads * 4);
+    if (chunks < 1) chunks = 1;
+    const size_t smem = payload_len <= kSmemPositions ? sizeof(int) * (size_t)payload_len : 0;
+    for (int f0 = 0; f0 < n_frames; f0 += 65535) {
+        const dim3 grid(chunks, (unsigned)((n_frames - f0) < 65535 ? (n_frames - f0) : 65535));
+        vote_counts_kernel<<<grid, threads, smem, stream>>>(raw_bits, words_per_frame, block_num, payload_len,
+                                                            pos_counts, f0);
+        B200WM_LAUNCH_CHECK("vote_counts_kernel");
+    }
+    return B200WM_OK;
+}
+
+// ---- per-frame finish -------------------------------------------------------------------------
+// One warp per frame.  m_i = count_i / n_i in float64 with n_i = number of block indices
+// congruent to i (de_shuffler.py:18: wm_bits[i::L].mean()), scattered through perm
+// (payload[payload_idx] = payload.copy(), :19), threshold 0.5*(max+min) (:20), strict > (:21).
+// IEEE fp64 division, addition and the exact halving give the same doubles as numpy.
+__global__ void __launch_bounds__(128) vote_finish_kernel(const int32_t* __restrict__ counts, int n_frames, int L,
+                                                          long long block_num, const int32_t* __restrict__ perm,
+                                                          uint8_t* __restrict__ patterns,
+                                                          unsigned long long* __restrict__ packed) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_frames) return;
+    const int32_t* cnt = counts + (long long)warp * L;
+    // an empty slice (payload_len > block_num) makes numpy's mean NaN; np.max/np.min then return
+    // NaN, the threshold is NaN and every comparison is False.
+    double vmax = -1.0, vmin = 2.0;
+    bool empty = false;
+    for (int i = lane; i < L; i += 32) {
+        const long long n = i < block_num ? (block_num - i + L - 1) / L : 0;
+        if (n > 0) {
+            const double m = (double)cnt[i] / (double)n;
+            vmax = fmax(vmax, m);
+            vmin = fmin(vmin, m);
+        } else {
+            empty = true;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        vmax = fmax(vmax, __shfl_xor_sync(0xFFFFFFFFu, vmax, s));
+        vmin = fmin(vmin, __shfl_xor_sync(0xFFFFFFFFu, vmin, s));
+    }
+    empty = __any_sync(0xFFFFFFFFu, empty);
+    const double thr = 0.5 * (vmax + vmin);
+    unsigned long long word = 0ull;
+    for (int i = lane; i < L; i += 32) {
+        const long long n = i < block_num ? (block_num - i + L - 1) / L : 0;
+        const int bit = (!empty && n > 0 && (double)cnt[i] / (double)n > thr) ? 1 : 0;
+        const int j = perm[i];
+        patterns[(long long)warp * L + j] = (uint8_t)bit;
+        if (L <= 64 && bit) word |= 1ull << (L - 1 - j);
+    }
+    if (packed) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) word |= __shfl_xor_sync(0xFFFFFFFFu, word, s);
+        if (lane == 0) packed[warp] = word;
+    }
+}
+
+int launch_vote_finish(const int32_t* pos_counts, int n_frames, int payload_len, long long block_num,
+                       const int32_t* perm, uint8_t* patterns, uint64_t* packed, cudaStream_t stream) {
+    if (!pos_counts || !perm || !patterns || n_frames < 0 || payload_len <= 0 || block_num < 0) return B200WM_ERR_INVALID;
+    if (packed && payload_len > 64) return B200WM_ERR_UNSUPPORTED;
+    if (n_frames == 0) return B200WM_OK;
+    const int threads = 128;
+    const long long blocks = ((long long)n_frames * 32 + threads - 1) / threads;
+    vote_finish_kernel<<<(unsigned)blocks, threads, 0, stream>>>(pos_counts, n_frames, payload_len, block_num, perm,
+                                                                patterns, (unsigned long long*)packed);
+    B200WM_LAUNCH_CHECK("vote_finish_kernel");
+    return B200WM_OK;
+}
+
+// ---- cross-frame pattern histogram ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) pattern_hist_kernel(const unsigned long long* __restrict__ packed,
+                                                           const int32_t* __restrict__ frame_segment,
+                                                           const int32_t* __restrict__ frame_order, int order_offset,
+                                                           int n_frames, int L, int n_segments, int32_t* hist,
+                                                           int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const int seg = frame_segment ? frame_segment[f] : 0;
+    if (seg < 0 || seg >= n_segments) return;
+    const unsigned long long p = packed[f];
+    const long long bin = (long long)seg * (1ll << L) + (long long)p;
+    atomicAdd(&hist[bin], 1);
+    atomicMin(&first_seen[bin], frame_order ? frame_order[f] : order_offset + f);
+    atomicAdd(&seg_frames[seg], 1);
+    for (int j = 0; j < L; ++j)
+        if ((p >> (L - 1 - j)) & 1ull) atomicAdd(&bit_votes[(long long)seg * L + j], 1);
+}
+
+int launch_pattern_hist(const uint64_t* packed, const int32_t* frame_segment, const int32_t* frame_order,
+                        int order_offset, int n_frames, int payload_len, int n_segments, int32_t* hist,
+                        int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames, cudaStream_t stream) {
+    if (!packed || !hist || !first_seen || !bit_votes || !seg_frames || n_frames < 0 || n_segments <= 0 || payload_len <= 0)
+        return B200WM_ERR_INVALID;
+    if (payload_len > 16) return B200WM_ERR_UNSUPPORTED;
+    if (n_frames == 0) return B200WM_OK;
+    const int threads = 256;
+    pattern_hist_kernel<<<(n_frames + threads - 1) / threads, threads, 0, stream>>>(
+        (const unsigned long long*)packed, frame_segment, frame_order, order_offset, n_frames, payload_len, n_segments,
+        hist, first_seen, bit_votes, seg_frames);
+    B200WM_LAUNCH_CHECK("pattern_hist_kernel");
+    return B200WM_OK;
+}
+
+}  // namespace b200wm

@@ -1,0 +1,17 @@
+"""B200 drop-in for ``offmark.degenerator.de_grayscale`` (src/offmark/degenerator/de_grayscale.py)."""
+import numpy as np
+
+from .de_shuffler import DeShuffler
+
+
+class DeGrayScale(DeShuffler):
+    """Same vote as ``DeShuffler`` over ``prod(shape)`` positions, returned as a 0/255 image
+    (de_grayscale.py:15-23)."""
+
+    def set_shape(self, payload_shape):
+        self.payload_shape = payload_shape
+        return super().set_shape(payload_shape)
+
+    def degenerate(self, wm_bits):
+        res = self._patterns(wm_bits)[0].cpu().numpy().astype(np.uint8) * 255
+        return res.reshape(self.payload_shape)

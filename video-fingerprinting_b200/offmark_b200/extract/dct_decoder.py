@@ -1,0 +1,23 @@
+"""B200 drop-in for ``offmark.extract.dct_decoder`` (src/offmark/extract/dct_decoder.py)."""
+import numpy as np
+
+from b200wm import ops
+from .._frames import FrameOnDevice, RawBits
+
+
+class DctDecoder:
+    """Same constructor and ``decode`` as the reference class (dct_decoder.py:4-27)."""
+
+    def __init__(self, key=None, alpha=20, device=None):
+        self.key = key
+        self.alpha = alpha
+        self.device = device
+
+    def decode(self, yuv):
+        frame = FrameOnDevice(yuv, self.device)
+        rows, cols, _ = frame.dev.shape
+        block_num = rows * cols // 8 // 8
+        masks = ops.dct8_masks(frame.dev, channel=0)
+        raw, _ = ops.dct8_extract(frame.dev, masks, alpha=self.alpha, channel=1)
+        bits = ops.unpack_bits(raw, block_num).astype(np.float64).reshape(1, -1)
+        return RawBits(bits, packed=raw, block_num=block_num)
