@@ -64,11 +64,18 @@ def test_dct8_embed_extract_vs_oracle(golden_dir, source):
     ops.dct8_embed_(t, masks, packed, n, alpha=20, channel=1)
     got = t.cpu().numpy()
     assert np.array_equal(got[:, :, 0], yuv0[:, :, 0]) and np.array_equal(got[:, :, 2], yuv0[:, :, 2])
-    # per-block agreement: a block can only differ when a mask threshold or the floor() in the
-    # quantiser is decided by float32 rounding inside cv2.dct; those are rare
+    # Per-block agreement.  Where |c21| is below float32 noise its SIGN is decided by rounding inside
+    # cv2.dct, and the embedder multiplies by np.sign(c21) (dct_encoder.py:33-35): such blocks get
+    # +step or -step (or stay unmarked when cv2 returns exactly 0) - equally readable marks, no
+    # independent implementation can reproduce the choice.  Everywhere else the blocks must agree,
+    # up to the rare mask-threshold ties.
     by, bx = frame.shape[0] // 8, frame.shape[1] // 8
+    c21 = o_dct._dct_all(yuv0[:, :, 1])[..., 2, 1]
     err = np.abs(got[:by * 8, :bx * 8, 1] - want[:by * 8, :bx * 8, 1]).reshape(by, 8, bx, 8).max(axis=(1, 3))
-    assert (err < 2e-3).mean() > 0.995, f"block agreement {(err < 2e-3).mean()}"
+    solid = np.abs(c21) > 1e-3
+    agree = (err < 2e-3)
+    assert agree[solid].mean() > 0.995, f"block agreement {agree[solid].mean()} on {solid.sum()} blocks"
+    assert agree.mean() > 0.97, f"overall block agreement {agree.mean()}"
     # extraction: our extractor on the reference's marked frame, and the reference's on ours
     bits_ref = o_dct.decode(want.copy())
     tw = torch.from_numpy(want).to(DEV)

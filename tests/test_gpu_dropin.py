@@ -108,7 +108,7 @@ def test_hls_pattern_collector_flow():
     dev = torch.device("cuda:0")
     S, F, h, w = 5, 12, 240, 320
     planes = torch.from_numpy(np.stack([synth.luma_plane_u8(h, w, f, 31) for f in range(S * F)])).to(dev)
-    seg_ids = [3, 77, 130, 255, 256]
+    seg_ids = [3, 77, 130, 254, 257]
     payloads = [o_pay.payload_for_segment(s) for s in seg_ids]
     enc, dec = DwtDctSvdEncoder(), DwtDctSvdDecoder()
     rows = np.stack([Shuffler(key=KEY).generate_wm(p, enc.wm_capacity((h, w, 3)))[0] for p in payloads])

@@ -165,16 +165,21 @@ __device__ __forceinline__ void basis21(float (&b1)[8], float (&b2)[8]) {
     b2[4] = -0.5f * C2; b2[5] = -0.5f * C6; b2[6] = 0.5f * C6; b2[7] = 0.5f * C2;
 }
 
+// Coefficient [2][1] through the same even/odd butterflies as the full transform: the row pass
+// takes differences x_k - x_{7-k} first and the column pass sums/differences of the row results,
+// so a block that is flat (or mirror-symmetric) along either axis gives EXACTLY 0, like cv2.dct.
+// That matters because the embedder multiplies by np.sign(c21) and sign(0) == 0 leaves such
+// blocks unmarked (dct_encoder.py:33-35).
 __device__ __forceinline__ float project21(const float (&b)[64], const float (&b1)[8], const float (&b2)[8]) {
-    float acc = 0.0f;
+    float h[8];
 #pragma unroll
     for (int y = 0; y < 8; ++y) {
-        float h = b[8 * y] * b1[0];
-#pragma unroll
-        for (int x = 1; x < 8; ++x) h = fmaf(b[8 * y + x], b1[x], h);
-        acc = fmaf(h, b2[y], acc);
+        const float d0 = b[8 * y] - b[8 * y + 7], d1 = b[8 * y + 1] - b[8 * y + 6];
+        const float d2 = b[8 * y + 2] - b[8 * y + 5], d3 = b[8 * y + 3] - b[8 * y + 4];
+        h[y] = fmaf(d3, b1[3], fmaf(d2, b1[2], fmaf(d1, b1[1], d0 * b1[0])));
     }
-    return acc;
+    const float s0 = h[0] + h[7], s1 = h[1] + h[6], s2 = h[2] + h[5], s3 = h[3] + h[4];
+    return fmaf(s0 - s3, b2[0], (s1 - s2) * b2[1]);
 }
 
 struct DctWm {

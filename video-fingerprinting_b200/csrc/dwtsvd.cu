@@ -27,10 +27,17 @@ constexpr int kThreads = 128;
 struct PlaneArgs {
     const uint8_t* src;
     uint8_t* dst;
-    long long pitch;          // bytes
     long long frame_stride;   // bytes
+    unsigned pitch;           // bytes (< 2^31: row addresses are one IMAD.WIDE each)
     int elem_stride;          // samples
 };
+
+__device__ __forceinline__ const uint8_t* row_ptr(const uint8_t* p, unsigned r, unsigned pitch) {
+    return p + (unsigned long long)r * pitch;
+}
+__device__ __forceinline__ uint8_t* row_ptr(uint8_t* p, unsigned r, unsigned pitch) {
+    return p + (unsigned long long)r * pitch;
+}
 
 struct EmbedArgs {
     const uint32_t* wm;       // [rows, wm_words]
@@ -52,9 +59,9 @@ struct ExtractArgs {
 // ------------------------------------------------------------------------------------------
 // Fast path: planar uint8, 8-byte aligned rows.  rows[r] keeps the raw bytes for the embed.
 template <bool kReadOnly>
-__device__ __forceinline__ void load_tile_u8(const uint8_t* p, long long pitch, uint2 (&rows)[8], float (&S)[16]) {
+__device__ __forceinline__ void load_tile_u8(const uint8_t* p, unsigned pitch, uint2 (&rows)[8], float (&S)[16]) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) rows[r] = kReadOnly ? ldg_nc_u2(p + r * pitch) : ldg_stream_u2(p + r * pitch);
+    for (int r = 0; r < 8; ++r) rows[r] = kReadOnly ? ldg_nc_u2(row_ptr(p, r, pitch)) : ldg_stream_u2(row_ptr(p, r, pitch));
     // float(2^23 + n) has n in its low mantissa bits: accumulate the four bytes of a 2x2 with
     // dp4a straight into that bit pattern, then one FADD removes the 2^23.
     constexpr unsigned kMagic = 0x4B000000u;
@@ -75,11 +82,11 @@ __device__ __forceinline__ void load_tile_u8(const uint8_t* p, long long pitch, 
 
 // Generic path: any dtype / stride / alignment.
 template <typename T>
-__device__ __forceinline__ void load_tile_generic(const uint8_t* p, long long pitch, int es, float (&S)[16]) {
+__device__ __forceinline__ void load_tile_generic(const uint8_t* p, unsigned pitch, int es, float (&S)[16]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const T* r0 = reinterpret_cast<const T*>(p + (2 * i) * pitch);
-        const T* r1 = reinterpret_cast<const T*>(p + (2 * i + 1) * pitch);
+        const T* r0 = reinterpret_cast<const T*>(row_ptr(p, 2 * i, pitch));
+        const T* r1 = reinterpret_cast<const T*>(row_ptr(p, 2 * i + 1, pitch));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float a = (float)r0[(2 * j) * es], b = (float)r0[(2 * j + 1) * es];
@@ -93,10 +100,19 @@ __device__ __forceinline__ void load_tile_generic(const uint8_t* p, long long pi
 // per-block quantisation
 // ------------------------------------------------------------------------------------------
 // Per-sample increment of each 2x2 of the tile for watermark bit `bit`: D[4*i+j] = (S'-S)[i][j]/4.
-__device__ __forceinline__ void embed_deltas(const float (&S)[16], int bit, float scale, float inv_scale,
-                                             float bias, float (&D)[16]) {
+// kStash: park S in shared memory while the eigen-iteration runs (4 STS.128 + 4 LDS.128 per
+// thread) instead of letting the compiler rebuild it from the pixel bytes under register pressure.
+template <bool kStash>
+__device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scale, float inv_scale,
+                                             float bias, float (&D)[16], float4* stash) {
     float v[4];
     bool zero;
+    if (kStash) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)   // asm: the compiler must not forward these stores to the loads below
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)),
+                         "f"(S[4 * i]), "f"(S[4 * i + 1]), "f"(S[4 * i + 2]), "f"(S[4 * i + 3]) : "memory");
+    }
     const float sigma = 0.5f * top_singular<true>(S, v, zero);   // sigma_0 of the LL block
     float q, rem;
     floor_divmod(sigma, scale, inv_scale, q, rem);
@@ -111,7 +127,12 @@ __device__ __forceinline__ void embed_deltas(const float (&S)[16], int bit, floa
     const float t = 0.25f * ((target - sigma) / sigma);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float sv = fmaf(S[4 * i + 3], v[3], fmaf(S[4 * i + 2], v[2], fmaf(S[4 * i + 1], v[1], S[4 * i] * v[0])));
+        float s0 = S[4 * i], s1 = S[4 * i + 1], s2 = S[4 * i + 2], s3 = S[4 * i + 3];
+        if (kStash) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s0), "=f"(s1), "=f"(s2), "=f"(s3)
+                         : "r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)) : "memory");
+        }
+        const float sv = fmaf(s3, v[3], fmaf(s2, v[2], fmaf(s1, v[1], s0 * v[0])));
         const float a = t * sv;
 #pragma unroll
         for (int j = 0; j < 4; ++j) D[4 * i + j] = fmaf(a, v[j], bias);
@@ -141,16 +162,17 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_kernel(PlaneArgs pl, Em
     const int row = em.frame_row ? em.frame_row[frame] : 0;
     const int bit = (em.wm[(long long)row * em.wm_words + (c >> 5)] >> (c & 31)) & 1;
 
-    const long long off = frame * pl.frame_stride + (long long)(ty * 8) * pl.pitch;
+    const long long off = frame * pl.frame_stride + (unsigned long long)(ty * 8) * pl.pitch;
     float S[16], D[16];
     if (kMode == 0) {
         const uint8_t* p = pl.src + off + tx * 8;
         uint8_t* o = pl.dst + off + tx * 8;
         uint2 rows[8];
+        __shared__ float4 s_stash[4 * kThreads];
         load_tile_u8<false>(p, pl.pitch, rows, S);
         // bias 1.5*2^23: the FMA rounds the increment to the nearest integer (ties to even) and
         // leaves it, two's complement, in the low mantissa bits.
-        embed_deltas(S, bit, em.scale, em.inv_scale, 12582912.0f, D);
+        embed_deltas<true>(S, bit, em.scale, em.inv_scale, 12582912.0f, D, s_stash + threadIdx.x);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             // 16-bit lanes: lo = increment of the left 2x2 of this word, hi = the right one
@@ -161,18 +183,18 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_kernel(PlaneArgs pl, Em
                 const uint2 w = rows[2 * i + rr];
                 uint2 out;
                 {
-                    const unsigned e = w.x & 0x00FF00FFu, od = (w.x >> 8) & 0x00FF00FFu;
+                    const unsigned e = __byte_perm(w.x, 0u, 0x4240), od = __byte_perm(w.x, 0u, 0x4341);
                     const unsigned e2 = __viaddmin_s16x2_relu(e, d01, 0x00FF00FFu);
                     const unsigned o2 = __viaddmin_s16x2_relu(od, d01, 0x00FF00FFu);
                     out.x = __byte_perm(e2, o2, 0x6240);
                 }
                 {
-                    const unsigned e = w.y & 0x00FF00FFu, od = (w.y >> 8) & 0x00FF00FFu;
+                    const unsigned e = __byte_perm(w.y, 0u, 0x4240), od = __byte_perm(w.y, 0u, 0x4341);
                     const unsigned e2 = __viaddmin_s16x2_relu(e, d23, 0x00FF00FFu);
                     const unsigned o2 = __viaddmin_s16x2_relu(od, d23, 0x00FF00FFu);
                     out.y = __byte_perm(e2, o2, 0x6240);
                 }
-                stg_stream_u2(o + (2 * i + rr) * pl.pitch, out);
+                stg_stream_u2(row_ptr(o, 2 * i + rr, pl.pitch), out);
             }
         }
     } else if (kMode == 1) {
@@ -180,24 +202,24 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_kernel(PlaneArgs pl, Em
         const uint8_t* p = pl.src + off + (long long)tx * 8 * es;
         uint8_t* o = pl.dst + off + (long long)tx * 8 * es;
         load_tile_generic<uint8_t>(p, pl.pitch, es, S);
-        embed_deltas(S, bit, em.scale, em.inv_scale, 0.0f, D);
+        embed_deltas<false>(S, bit, em.scale, em.inv_scale, 0.0f, D, nullptr);
 #pragma unroll
         for (int y = 0; y < 8; ++y)
 #pragma unroll
             for (int x = 0; x < 8; ++x) {
-                const float f = (float)p[y * pl.pitch + x * es] + D[4 * (y >> 1) + (x >> 1)];
-                o[y * pl.pitch + x * es] = (uint8_t)__float2int_rn(fminf(fmaxf(f, 0.0f), 255.0f));
+                const float f = (float)row_ptr(p, y, pl.pitch)[x * es] + D[4 * (y >> 1) + (x >> 1)];
+                row_ptr(o, y, pl.pitch)[x * es] = (uint8_t)__float2int_rn(fminf(fmaxf(f, 0.0f), 255.0f));
             }
     } else {
         const int es = pl.elem_stride;
         const uint8_t* p = pl.src + off + (long long)tx * 8 * es * 4;
         uint8_t* o = pl.dst + off + (long long)tx * 8 * es * 4;
         load_tile_generic<float>(p, pl.pitch, es, S);
-        embed_deltas(S, bit, em.scale, em.inv_scale, 0.0f, D);
+        embed_deltas<false>(S, bit, em.scale, em.inv_scale, 0.0f, D, nullptr);
 #pragma unroll
         for (int y = 0; y < 8; ++y) {
-            const float* pr = reinterpret_cast<const float*>(p + y * pl.pitch);
-            float* orow = reinterpret_cast<float*>(o + y * pl.pitch);
+            const float* pr = reinterpret_cast<const float*>(row_ptr(p, y, pl.pitch));
+            float* orow = reinterpret_cast<float*>(row_ptr(o, y, pl.pitch));
 #pragma unroll
             for (int x = 0; x < 8; ++x) orow[x * es] = pr[x * es] + D[4 * (y >> 1) + (x >> 1)];
         }
@@ -214,7 +236,7 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_extract_kernel(PlaneArgs pl, 
     if (c < (unsigned)g.n_tiles) {
         const unsigned ty = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
         const unsigned tx = c - ty * g.tiles_x;
-        const long long off = frame * pl.frame_stride + (long long)(ty * 8) * pl.pitch;
+        const long long off = frame * pl.frame_stride + (unsigned long long)(ty * 8) * pl.pitch;
         float S[16];
         if (kMode == 0) {
             uint2 rows[8];
@@ -267,7 +289,7 @@ int validate_plane(const b200wm_plane* pl) {
     const long long esz = pl->dtype == B200WM_U8 ? 1 : 4;
     if (pl->pitch_bytes < (long long)pl->width * pl->elem_stride * esz - (pl->elem_stride - 1) * esz) return B200WM_ERR_INVALID;
     if (pl->dtype == B200WM_F32 && (pl->pitch_bytes % 4 || pl->frame_stride_bytes % 4)) return B200WM_ERR_INVALID;
-    if ((long long)pl->height * pl->width / 64 >= (1ll << 26)) return B200WM_ERR_UNSUPPORTED;
+    if ((long long)pl->height * pl->width / 64 >= (1ll << 26) || pl->pitch_bytes >= (1ll << 31)) return B200WM_ERR_UNSUPPORTED;
     return B200WM_OK;
 }
 
@@ -280,7 +302,7 @@ int launch_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* pl, cons
     if (wm_len < g.n_tiles || (long long)wm_words * 32 < g.n_tiles) return B200WM_ERR_SHORT_WM;
     if (g.n_tiles == 0 || pl->n_frames == 0) return B200WM_OK;
     if ((uintptr_t)src % 4 && pl->dtype == B200WM_F32) return B200WM_ERR_INVALID;
-    PlaneArgs pa{(const uint8_t*)src, (uint8_t*)dst, pl->pitch_bytes, pl->frame_stride_bytes, pl->elem_stride};
+    PlaneArgs pa{(const uint8_t*)src, (uint8_t*)dst, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
     EmbedArgs ea{wm, frame_row, wm_words, scale, 1.0f / scale};
     const int mode = plane_mode(src, dst, pl);
     const unsigned gx = (g.n_tiles + kThreads - 1) / kThreads;
@@ -312,7 +334,7 @@ int launch_dwtsvd_extract(const void* src, const b200wm_plane* pl, float scale, 
     if (pos_counts && fused)
         B200WM_CUDA_TRY(cudaMemsetAsync(pos_counts, 0, sizeof(int32_t) * (size_t)pl->n_frames * payload_len, stream));
     if (g.words > 0) {
-        PlaneArgs pa{(const uint8_t*)src, nullptr, pl->pitch_bytes, pl->frame_stride_bytes, pl->elem_stride};
+        PlaneArgs pa{(const uint8_t*)src, nullptr, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
         ExtractArgs xa{raw_bits, fused ? pos_counts : nullptr, sigma, payload_len, scale, 1.0f / scale};
         const int mode = plane_mode(src, src, pl);
         const unsigned gx = ((unsigned)g.words * 32 + kThreads - 1) / kThreads;

@@ -53,7 +53,14 @@ __device__ __forceinline__ float dot4(const float (&a)[4], const float (&b)[4]) 
 // out[4] = sigma_0 = sqrt of that eigenvalue, rounded once from fp64.
 // Deliberately rolled loops over local-memory arrays: this function must not raise the register
 // footprint of the kernels that call it once in a few thousand blocks.
-__device__ __noinline__ void top_pair_jacobi(const float* __restrict__ S, float* __restrict__ out) {
+struct Top5 { float v0, v1, v2, v3, sigma; };
+
+__device__ __noinline__ Top5 top_pair_jacobi(float s0, float s1, float s2, float s3, float s4, float s5, float s6, float s7,
+                                             float s8, float s9, float s10, float s11, float s12, float s13, float s14,
+                                             float s15) {
+    // arguments arrive by value so that the caller's block never has its address taken
+    float S[16] = {s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15};
+    float out[5];
     double A[16], V[16];
 #pragma unroll 1
     for (int i = 0; i < 4; ++i)
@@ -114,6 +121,23 @@ __device__ __noinline__ void top_pair_jacobi(const float* __restrict__ S, float*
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) out[k] = (float)(V[4 * k + best] * n);
     out[4] = (float)sqrt(lam > 0.0 ? lam : 0.0);
+    return Top5{out[0], out[1], out[2], out[3], out[4]};
+}
+
+// One power step with the convergence test.  x is the current iterate, w = G x.
+// Returns true when the Kato-Temple bound certifies lambda (see the header comment).
+__device__ __forceinline__ bool rayleigh_check(const float (&x)[4], const float (&w)[4], float tr, float& xw, float& xx) {
+    xw = dot4(x, w);
+    xx = dot4(x, x);
+    float lam;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(lam) : "f"(xx));
+    lam *= xw;
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = fmaf(-lam, x[k], w[k]);
+    const float rr = dot4(r, r);
+    const float gap = fmaf(2.0f, lam, -tr);
+    return (gap > 0.0f) && (rr <= kTau * lam * gap * xx);
 }
 
 // sigma0 = largest singular value of S (not squared); v = unit right singular vector.
@@ -121,42 +145,41 @@ template <bool kWantVec>
 __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4], bool& zero_block) {
     float G[10];
     gram4(S, G);
-    const float tr = (G[0] + G[4]) + (G[7] + G[9]);
-    zero_block = !(tr > 0.0f);
+    const float tr_raw = (G[0] + G[4]) + (G[7] + G[9]);
+    zero_block = !(tr_raw > 0.0f);
     if (zero_block) {
         v[0] = v[1] = v[2] = v[3] = 0.0f;
         return 0.0f;
     }
-    const float rtr = __frcp_rn(tr);
-    float x[4];
-    x[0] = ((G[0] + G[1]) + (G[2] + G[3])) * rtr;
-    x[1] = ((G[1] + G[4]) + (G[5] + G[6])) * rtr;
-    x[2] = ((G[2] + G[5]) + (G[7] + G[8])) * rtr;
-    x[3] = ((G[3] + G[6]) + (G[8] + G[9])) * rtr;
+    // Exact power-of-two normalisation: tr = tr_raw * 2^-(e+1) lies in [0.5, 1), so the iterates
+    // need no rescaling and nothing is rounded (G stays exact for uint8 input).
+    const unsigned ebits = __float_as_uint(tr_raw) & 0x7F800000u;
+    const float down = __uint_as_float(0x7E800000u - ebits);
+    const float up = __uint_as_float(ebits + 0x00800000u);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) G[k] *= down;
+    const float tr = tr_raw * down;
 
-    bool done = false;
-    float xw = 0.0f, xx = 1.0f;
+    float x[4], w[4];
+    w[0] = (G[0] + G[1]) + (G[2] + G[3]);       // G * ones
+    w[1] = (G[1] + G[4]) + (G[5] + G[6]);
+    w[2] = (G[2] + G[5]) + (G[7] + G[8]);
+    w[3] = (G[3] + G[6]) + (G[8] + G[9]);
+    symv4(G, w, x);                              // second power step, unchecked: one step alone almost never certifies
+    symv4(G, x, w);
+    float xw, xx;
+    bool done = rayleigh_check(x, w, tr, xw, xx);
+    if (!done) {
 #pragma unroll 1
-    for (int it = 0; it < kPowerIters; ++it) {
-        float w[4];
-        symv4(G, x, w);
-        xw = dot4(x, w);
-        xx = dot4(x, x);
-        float lam;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(lam) : "f"(xx));
-        lam *= xw;
-        float r[4];
+        for (int it = 0; it < kPowerIters && !done; ++it) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) r[k] = fmaf(-lam, x[k], w[k]);
-        const float rr = dot4(r, r);
-        const float gap = fmaf(2.0f, lam, -tr);
-        done = (gap > 0.0f) && (rr <= kTau * lam * gap * xx);
-        if (done) break;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) x[k] = w[k] * rtr;
+            for (int k = 0; k < 4; ++k) x[k] = w[k];
+            symv4(G, x, w);
+            done = rayleigh_check(x, w, tr, xw, xx);
+        }
     }
     if (done) {
-        const float lam = xw / xx;                 // IEEE division: this is the result
+        const float lam = (xw / xx) * up;          // IEEE division: this is the result
         if (kWantVec) {
             const float n = rsqrtf(xx);
 #pragma unroll
@@ -164,14 +187,10 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
         }
         return sqrtf(lam);
     }
-    // copy so that S itself never has its address taken (keeps it in registers on the hot path)
-    float Sc[16], vj[5];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) Sc[k] = S[k];
-    top_pair_jacobi(Sc, vj);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = vj[k];
-    return vj[4];
+    const Top5 t = top_pair_jacobi(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8], S[9], S[10], S[11], S[12],
+                                   S[13], S[14], S[15]);
+    v[0] = t.v0; v[1] = t.v1; v[2] = t.v2; v[3] = t.v3;
+    return t.sigma;
 }
 
 }  // namespace b200wm
