@@ -54,6 +54,8 @@ def parse_args():
     p.add_argument("--cpu-frames-per-core", type=int, default=1)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--path", type=int, default=0, choices=[0, 1],
+                   help="0: TMA-staged persistent kernels (default), 1: vectorised-load kernels (A/B evidence)")
     return p.parse_args()
 
 
@@ -224,6 +226,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    ops.set_path(args.path)
     n_frames = args.frames
     n_seg_local = (n_frames + SEGMENT_FRAMES - 1) // SEGMENT_FRAMES
     n_seg_global = n_seg_local * world
@@ -312,7 +315,8 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     embed_gbs = 2.0 * W * H * n_frames / (k_embed * 1e-3) / 1e9
     extract_gbs = 1.0 * W * H * n_frames / (k_extract * 1e-3) / 1e9
-    dominant = "dwtsvd_embed_kernel" if k_embed >= k_extract else "dwtsvd_extract_kernel"
+    suffix = "_tma_kernel" if args.path == 0 else "_kernel"
+    dominant = ("dwtsvd_embed" if k_embed >= k_extract else "dwtsvd_extract") + suffix
     achieved = embed_gbs if k_embed >= k_extract else extract_gbs
     step_gbs = 3.0 * W * H * n_frames / (ms_per_step * 1e-3) / 1e9
 
@@ -321,6 +325,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, n_frames),
         "gpu_launches": launches, "clocks": clocks,
+        "kernel_path": "tma_persistent" if args.path == 0 else "ldg_vectorised",
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": (2 if dominant.startswith("dwtsvd_embed") else 1) * W * H * n_frames},

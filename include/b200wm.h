@@ -88,6 +88,14 @@ B200WM_API const char* b200wm_strerror(int status);
 B200WM_API const char* b200wm_last_cuda_error(void);         /* thread-local; "" if none */
 B200WM_API int         b200wm_device_ok(void);               /* 0 if the current device can run the kernels */
 B200WM_API int         b200wm_kernel_launches(void);         /* kernels launched by this library since load (process-wide) */
+/*
+ * Kernel path for the DWT/SVD pair: 0 = automatic (TMA-staged persistent kernels when the plane
+ * is planar uint8 with base, pitch and frame stride multiples of 16 bytes and >= 256 columns;
+ * vectorised-load kernels otherwise), 1 = always the vectorised-load kernels.  Results are
+ * identical; the switch exists so both paths can be measured and tested.  Process-wide.
+ */
+B200WM_API int         b200wm_set_path(int path);
+B200WM_API int         b200wm_get_path(void);
 
 /* ---- geometry helpers (host, pure arithmetic) ------------------------------------ */
 /* DwtDctSvdEncoder.wm_capacity (embed/dwt_dct_svd_encoder.py:14-17): height*width/64. */

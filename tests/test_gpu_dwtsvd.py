@@ -12,6 +12,15 @@ from parity import PAYLOAD, KEY, knife_edge_blocks, tile_mask_to_pixels
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["tma", "ldg"])
+def kernel_path(request):
+    """Every test runs on both kernel families: TMA-staged persistent (auto) and vectorised loads."""
+    from b200wm import ops
+    ops.set_path(request.param)
+    yield request.param
+    ops.set_path(0)
+
+
 def _dev():
     return torch.device("cuda:0")
 

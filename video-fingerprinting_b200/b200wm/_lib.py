@@ -32,6 +32,8 @@ PROTOTYPES = {
     "b200wm_last_cuda_error": (C.c_char_p, []),
     "b200wm_device_ok": (C.c_int, []),
     "b200wm_kernel_launches": (C.c_int, []),
+    "b200wm_set_path": (C.c_int, [C.c_int]),
+    "b200wm_get_path": (C.c_int, []),
     "b200wm_block_num": (_i64, [C.c_int, C.c_int]),
     "b200wm_tile_count": (_i64, [C.c_int, C.c_int]),
     "b200wm_words_per_frame": (_i32, [C.c_int, C.c_int]),

@@ -257,5 +257,14 @@ def yuv32_to_bgr8(yuv):
     return out
 
 
+def set_path(path):
+    """0 = automatic (TMA-staged kernels when the planes qualify), 1 = vectorised-load kernels only."""
+    check(lib.b200wm_set_path(int(path)))
+
+
+def get_path():
+    return int(lib.b200wm_get_path())
+
+
 def kernel_launches():
     return int(lib.b200wm_kernel_launches())

@@ -27,6 +27,8 @@ int launch_dct8_embed(const void*, void*, const b200wm_plane*, const float*, con
 int launch_dct8_extract(const void*, const b200wm_plane*, const float*, const float*, const double*, float, uint32_t*, int,
                         int, int32_t*, cudaStream_t);
 int launch_bgr8_to_yuv32(const uint8_t*, float*, long long, cudaStream_t);
+void set_path(int);
+int get_path();
 int launch_yuv32_to_bgr8(const float*, uint8_t*, long long, cudaStream_t);
 
 }  // namespace b200wm
@@ -62,6 +64,13 @@ B200WM_API int b200wm_device_ok(void) {
 }
 
 B200WM_API int b200wm_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+B200WM_API int b200wm_set_path(int path) {
+    if (path != 0 && path != 1) return B200WM_ERR_INVALID;
+    set_path(path);
+    return B200WM_OK;
+}
+B200WM_API int b200wm_get_path(void) { return get_path(); }
 
 B200WM_API int64_t b200wm_block_num(int height, int width) { return (int64_t)height * width / 64; }
 B200WM_API int64_t b200wm_tile_count(int height, int width) {

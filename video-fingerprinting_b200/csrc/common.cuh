@@ -65,14 +65,33 @@ __device__ __forceinline__ void stg_stream_u2(void* p, uint2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
+// a / b and sqrt(a) for positive normal operands: hardware approximation plus one Newton step.
+// Within 1 ulp (almost always correctly rounded) and, unlike the IEEE routines, straight-line
+// code with no slow-path branch.
+__device__ __forceinline__ float div_pos(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    const float q = a * r;
+    return fmaf(fmaf(-q, b, a), r, q);
+}
+__device__ __forceinline__ float sqrt_pos(float a) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    const float s = a * r;
+    return fmaf(fmaf(-s, s, a) * 0.5f, r, s);
+}
+
 // exact float32 remainder of a non-negative x by a positive m, and the floor quotient
 // (numpy's float `%` and `//` on positive operands: embed/dwt_dct_svd_encoder.py:44,
-// extract/dwt_dct_svd_decoder.py:36).  Valid while x/m < 2^23.
+// extract/dwt_dct_svd_decoder.py:36).  Valid while x/m < 2^23.  Branch-free: the quotient
+// estimate is off by at most one, fixed with selects, and the remainder of the TRUE floor is
+// exactly representable, so the final FMA is exact.
 __device__ __forceinline__ void floor_divmod(float x, float m, float inv_m, float& q, float& r) {
     q = floorf(x * inv_m);
-    r = fmaf(-m, q, x);              // exact when q is the true floor
-    if (r < 0.0f) { q -= 1.0f; r = fmaf(-m, q, x); }
-    else if (r >= m) { q += 1.0f; r = fmaf(-m, q, x); }
+    r = fmaf(-m, q, x);
+    const float fix = r < 0.0f ? -1.0f : (r >= m ? 1.0f : 0.0f);
+    q += fix;
+    r = fmaf(-m, q, x);
 }
 
 }  // namespace b200wm

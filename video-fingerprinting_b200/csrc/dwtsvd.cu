@@ -19,134 +19,9 @@
 // algorithmic bytes per frame are W*H (extract) and 2*W*H (embed), see DESIGN.md.
 #include "common.cuh"
 #include "svd4.cuh"
+#include "dwtsvd_tile.cuh"
 
 namespace b200wm {
-
-constexpr int kThreads = 128;
-
-struct PlaneArgs {
-    const uint8_t* src;
-    uint8_t* dst;
-    long long frame_stride;   // bytes
-    unsigned pitch;           // bytes (< 2^31: row addresses are one IMAD.WIDE each)
-    int elem_stride;          // samples
-};
-
-__device__ __forceinline__ const uint8_t* row_ptr(const uint8_t* p, unsigned r, unsigned pitch) {
-    return p + (unsigned long long)r * pitch;
-}
-__device__ __forceinline__ uint8_t* row_ptr(uint8_t* p, unsigned r, unsigned pitch) {
-    return p + (unsigned long long)r * pitch;
-}
-
-struct EmbedArgs {
-    const uint32_t* wm;       // [rows, wm_words]
-    const int32_t* frame_row; // nullable
-    int wm_words;
-    float scale, inv_scale;
-};
-
-struct ExtractArgs {
-    uint32_t* raw_bits;       // [n_frames, words]
-    int32_t* pos_counts;      // nullable, [n_frames, payload_len]; only when 32 % payload_len == 0
-    float* sigma;             // nullable debug output [n_frames, n_tiles]
-    int payload_len;
-    float scale, inv_scale;
-};
-
-// ------------------------------------------------------------------------------------------
-// tile loaders: produce S[16] (2x2 sums, row-major over the 4x4 block)
-// ------------------------------------------------------------------------------------------
-// Fast path: planar uint8, 8-byte aligned rows.  rows[r] keeps the raw bytes for the embed.
-template <bool kReadOnly>
-__device__ __forceinline__ void load_tile_u8(const uint8_t* p, unsigned pitch, uint2 (&rows)[8], float (&S)[16]) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) rows[r] = kReadOnly ? ldg_nc_u2(row_ptr(p, r, pitch)) : ldg_stream_u2(row_ptr(p, r, pitch));
-    // float(2^23 + n) has n in its low mantissa bits: accumulate the four bytes of a 2x2 with
-    // dp4a straight into that bit pattern, then one FADD removes the 2^23.
-    constexpr unsigned kMagic = 0x4B000000u;
-    constexpr float kMagicF = 8388608.0f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint2 a = rows[2 * i], b = rows[2 * i + 1];
-        unsigned s0 = __dp4a(a.x, 0x00000101u, kMagic); s0 = __dp4a(b.x, 0x00000101u, s0);
-        unsigned s1 = __dp4a(a.x, 0x01010000u, kMagic); s1 = __dp4a(b.x, 0x01010000u, s1);
-        unsigned s2 = __dp4a(a.y, 0x00000101u, kMagic); s2 = __dp4a(b.y, 0x00000101u, s2);
-        unsigned s3 = __dp4a(a.y, 0x01010000u, kMagic); s3 = __dp4a(b.y, 0x01010000u, s3);
-        S[4 * i + 0] = __uint_as_float(s0) - kMagicF;
-        S[4 * i + 1] = __uint_as_float(s1) - kMagicF;
-        S[4 * i + 2] = __uint_as_float(s2) - kMagicF;
-        S[4 * i + 3] = __uint_as_float(s3) - kMagicF;
-    }
-}
-
-// Generic path: any dtype / stride / alignment.
-template <typename T>
-__device__ __forceinline__ void load_tile_generic(const uint8_t* p, unsigned pitch, int es, float (&S)[16]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const T* r0 = reinterpret_cast<const T*>(row_ptr(p, 2 * i, pitch));
-        const T* r1 = reinterpret_cast<const T*>(row_ptr(p, 2 * i + 1, pitch));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float a = (float)r0[(2 * j) * es], b = (float)r0[(2 * j + 1) * es];
-            const float c = (float)r1[(2 * j) * es], d = (float)r1[(2 * j + 1) * es];
-            S[4 * i + j] = (a + b) + (c + d);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// per-block quantisation
-// ------------------------------------------------------------------------------------------
-// Per-sample increment of each 2x2 of the tile for watermark bit `bit`: D[4*i+j] = (S'-S)[i][j]/4.
-// kStash: park S in shared memory while the eigen-iteration runs (4 STS.128 + 4 LDS.128 per
-// thread) instead of letting the compiler rebuild it from the pixel bytes under register pressure.
-template <bool kStash>
-__device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scale, float inv_scale,
-                                             float bias, float (&D)[16], float4* stash) {
-    float v[4];
-    bool zero;
-    if (kStash) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)   // asm: the compiler must not forward these stores to the loads below
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)),
-                         "f"(S[4 * i]), "f"(S[4 * i + 1]), "f"(S[4 * i + 2]), "f"(S[4 * i + 3]) : "memory");
-    }
-    const float sigma = 0.5f * top_singular<true>(S, v, zero);   // sigma_0 of the LL block
-    float q, rem;
-    floor_divmod(sigma, scale, inv_scale, q, rem);
-    const float target = (q + 0.25f + 0.5f * (float)bit) * scale;
-    if (zero) {
-        // svd(0) = (I, 0, I): the reference puts sigma_0' on DCT coefficient [0][0], i.e. a flat
-        // block target/4 in the LL band -> target/8 on every sample.
-#pragma unroll
-        for (int k = 0; k < 16; ++k) D[k] = fmaf(target, 0.125f, bias);
-        return;
-    }
-    const float t = 0.25f * ((target - sigma) / sigma);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float s0 = S[4 * i], s1 = S[4 * i + 1], s2 = S[4 * i + 2], s3 = S[4 * i + 3];
-        if (kStash) {
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s0), "=f"(s1), "=f"(s2), "=f"(s3)
-                         : "r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)) : "memory");
-        }
-        const float sv = fmaf(s3, v[3], fmaf(s2, v[2], fmaf(s1, v[1], s0 * v[0])));
-        const float a = t * sv;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) D[4 * i + j] = fmaf(a, v[j], bias);
-    }
-}
-
-__device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, float inv_scale, float& sigma) {
-    float v[4];
-    bool zero;
-    sigma = 0.5f * top_singular<false>(S, v, zero);
-    float q, rem;
-    floor_divmod(sigma, scale, inv_scale, q, rem);
-    return rem > 0.5f * scale ? 1 : 0;
-}
 
 // ------------------------------------------------------------------------------------------
 // kernels
@@ -180,20 +55,7 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_kernel(PlaneArgs pl, Em
             const unsigned d23 = __byte_perm(__float_as_uint(D[4 * i + 2]), __float_as_uint(D[4 * i + 3]), 0x5410);
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
-                const uint2 w = rows[2 * i + rr];
-                uint2 out;
-                {
-                    const unsigned e = __byte_perm(w.x, 0u, 0x4240), od = __byte_perm(w.x, 0u, 0x4341);
-                    const unsigned e2 = __viaddmin_s16x2_relu(e, d01, 0x00FF00FFu);
-                    const unsigned o2 = __viaddmin_s16x2_relu(od, d01, 0x00FF00FFu);
-                    out.x = __byte_perm(e2, o2, 0x6240);
-                }
-                {
-                    const unsigned e = __byte_perm(w.y, 0u, 0x4240), od = __byte_perm(w.y, 0u, 0x4341);
-                    const unsigned e2 = __viaddmin_s16x2_relu(e, d23, 0x00FF00FFu);
-                    const unsigned o2 = __viaddmin_s16x2_relu(od, d23, 0x00FF00FFu);
-                    out.y = __byte_perm(e2, o2, 0x6240);
-                }
+                const uint2 out = add_clamp_row(rows[2 * i + rr], d01, d23);
                 stg_stream_u2(row_ptr(o, 2 * i + rr, pl.pitch), out);
             }
         }
@@ -262,8 +124,7 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_extract_kernel(PlaneArgs pl, 
         if (threadIdx.x < 32) cta_counts[threadIdx.x] = 0;
         __syncthreads();
         if ((int)lane < L) {
-            const unsigned every = L == 32 ? 1u : (0xFFFFFFFFu / ((1u << L) - 1u));
-            const int n = __popc(ballot & (every << lane));
+            const int n = __popc(ballot & (ex.every << lane));
             if (n) atomicAdd(&cta_counts[lane], n);
         }
         __syncthreads();
@@ -275,6 +136,17 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_extract_kernel(PlaneArgs pl, 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const TileGeom& g);
+int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const TileGeom& g, ExtractArgs xa, cudaStream_t stream);
+int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, const TileGeom& g, EmbedArgs ea,
+                            cudaStream_t stream);
+
+// Path selection: 0 = automatic (TMA when the plane qualifies), 1 = force the LDG kernels.
+// Set through b200wm_set_path() for A/B measurements; results are identical either way.
+static int g_path = 0;
+void set_path(int p) { g_path = p; }
+int get_path() { return g_path; }
+
 static int plane_mode(const void* a, const void* b, const b200wm_plane* pl) {
     if (pl->dtype == B200WM_F32) return 2;
     const bool aligned = pl->elem_stride == 1 && (pl->pitch_bytes % 8) == 0 && (pl->frame_stride_bytes % 8) == 0 &&
@@ -304,6 +176,7 @@ int launch_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* pl, cons
     if ((uintptr_t)src % 4 && pl->dtype == B200WM_F32) return B200WM_ERR_INVALID;
     PlaneArgs pa{(const uint8_t*)src, (uint8_t*)dst, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
     EmbedArgs ea{wm, frame_row, wm_words, scale, 1.0f / scale};
+    if (g_path == 0 && tma_eligible(src, dst, pl, g)) return launch_dwtsvd_embed_tma(src, dst, pl, g, ea, stream);
     const int mode = plane_mode(src, dst, pl);
     const unsigned gx = (g.n_tiles + kThreads - 1) / kThreads;
     for (int f0 = 0; f0 < pl->n_frames; f0 += 65535) {
@@ -335,7 +208,16 @@ int launch_dwtsvd_extract(const void* src, const b200wm_plane* pl, float scale, 
         B200WM_CUDA_TRY(cudaMemsetAsync(pos_counts, 0, sizeof(int32_t) * (size_t)pl->n_frames * payload_len, stream));
     if (g.words > 0) {
         PlaneArgs pa{(const uint8_t*)src, nullptr, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
-        ExtractArgs xa{raw_bits, fused ? pos_counts : nullptr, sigma, payload_len, scale, 1.0f / scale};
+        ExtractArgs xa{raw_bits, fused ? pos_counts : nullptr, sigma, payload_len, fused ? every_mask(payload_len) : 0u, scale, 1.0f / scale};
+        if (g_path == 0 && !sigma && tma_eligible(src, src, pl, g)) {
+            // strips OR their bits into the packed words; surplus words must read 0
+            B200WM_CUDA_TRY(cudaMemsetAsync(raw_bits, 0, sizeof(uint32_t) * (size_t)pl->n_frames * g.words, stream));
+            rc = launch_dwtsvd_extract_tma(src, pl, g, xa, stream);
+            if (rc) return rc;
+            if (pos_counts && !fused)
+                return launch_vote_counts(raw_bits, pl->n_frames, words_per_frame, g.block_num, payload_len, pos_counts, stream);
+            return B200WM_OK;
+        }
         const int mode = plane_mode(src, src, pl);
         const unsigned gx = ((unsigned)g.words * 32 + kThreads - 1) / kThreads;
         for (int f0 = 0; f0 < pl->n_frames; f0 += 65535) {

@@ -1,0 +1,167 @@
+// Per-tile pieces shared by the LDG kernels (dwtsvd.cu) and the TMA kernels (dwtsvd_tma.cu).
+#pragma once
+#include "common.cuh"
+#include "svd4.cuh"
+
+namespace b200wm {
+
+constexpr int kThreads = 128;
+
+struct PlaneArgs {
+    const uint8_t* src;
+    uint8_t* dst;
+    long long frame_stride;   // bytes
+    unsigned pitch;           // bytes (< 2^31: row addresses are one IMAD.WIDE each)
+    int elem_stride;          // samples
+};
+
+__device__ __forceinline__ const uint8_t* row_ptr(const uint8_t* p, unsigned r, unsigned pitch) {
+    return p + (unsigned long long)r * pitch;
+}
+__device__ __forceinline__ uint8_t* row_ptr(uint8_t* p, unsigned r, unsigned pitch) {
+    return p + (unsigned long long)r * pitch;
+}
+
+struct EmbedArgs {
+    const uint32_t* wm;       // [rows, wm_words]
+    const int32_t* frame_row; // nullable
+    int wm_words;
+    float scale, inv_scale;
+};
+
+struct ExtractArgs {
+    uint32_t* raw_bits;       // [n_frames, words]
+    int32_t* pos_counts;      // nullable, [n_frames, payload_len]; only when 32 % payload_len == 0
+    float* sigma;             // nullable debug output [n_frames, n_tiles]
+    int payload_len;
+    unsigned every;           // bit i*payload_len set for every i (payload_len divides 32), else 0
+    float scale, inv_scale;
+};
+
+inline unsigned every_mask(int payload_len) {
+    if (payload_len <= 0 || payload_len > 32 || 32 % payload_len) return 0u;
+    return payload_len == 32 ? 1u : (0xFFFFFFFFu / ((1u << payload_len) - 1u));
+}
+
+// ------------------------------------------------------------------------------------------
+// tile loaders: produce S[16] (2x2 sums, row-major over the 4x4 block)
+// ------------------------------------------------------------------------------------------
+// Fast path: planar uint8, 8-byte aligned rows.  rows[r] keeps the raw bytes for the embed.
+// S[4*i+j] = sum of the 2x2 samples (rows 2i,2i+1; columns 2j,2j+1) of an 8x8 uint8 tile.
+__device__ __forceinline__ void sums_from_rows(const uint2 (&rows)[8], float (&S)[16]) {
+    // float(2^23 + n) has n in its low mantissa bits: accumulate the four bytes of a 2x2 with
+    // dp4a straight into that bit pattern, then one FADD removes the 2^23.
+    constexpr unsigned kMagic = 0x4B000000u;
+    constexpr float kMagicF = 8388608.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint2 a = rows[2 * i], b = rows[2 * i + 1];
+        unsigned s0 = __dp4a(a.x, 0x00000101u, kMagic); s0 = __dp4a(b.x, 0x00000101u, s0);
+        unsigned s1 = __dp4a(a.x, 0x01010000u, kMagic); s1 = __dp4a(b.x, 0x01010000u, s1);
+        unsigned s2 = __dp4a(a.y, 0x00000101u, kMagic); s2 = __dp4a(b.y, 0x00000101u, s2);
+        unsigned s3 = __dp4a(a.y, 0x01010000u, kMagic); s3 = __dp4a(b.y, 0x01010000u, s3);
+        S[4 * i + 0] = __uint_as_float(s0) - kMagicF;
+        S[4 * i + 1] = __uint_as_float(s1) - kMagicF;
+        S[4 * i + 2] = __uint_as_float(s2) - kMagicF;
+        S[4 * i + 3] = __uint_as_float(s3) - kMagicF;
+    }
+}
+
+template <bool kReadOnly>
+__device__ __forceinline__ void load_tile_u8(const uint8_t* p, unsigned pitch, uint2 (&rows)[8], float (&S)[16]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) rows[r] = kReadOnly ? ldg_nc_u2(row_ptr(p, r, pitch)) : ldg_stream_u2(row_ptr(p, r, pitch));
+    sums_from_rows(rows, S);
+}
+
+// One row of a tile (8 uint8 samples in a uint2) plus the integer increments of its four 2x2
+// columns, saturated to [0, 255].  d01 / d23 hold two increments each as int16 lanes; the bytes
+// are widened to int16 lanes (even / odd samples), added and clamped with one DPX instruction
+// per pair (VIADDMNMX.S16x2.RELU) and narrowed back.
+__device__ __forceinline__ uint2 add_clamp_row(uint2 w, unsigned d01, unsigned d23) {
+    uint2 out;
+    {
+        const unsigned e = __byte_perm(w.x, 0u, 0x4240), od = __byte_perm(w.x, 0u, 0x4341);
+        const unsigned e2 = __viaddmin_s16x2_relu(e, d01, 0x00FF00FFu);
+        const unsigned o2 = __viaddmin_s16x2_relu(od, d01, 0x00FF00FFu);
+        out.x = __byte_perm(e2, o2, 0x6240);
+    }
+    {
+        const unsigned e = __byte_perm(w.y, 0u, 0x4240), od = __byte_perm(w.y, 0u, 0x4341);
+        const unsigned e2 = __viaddmin_s16x2_relu(e, d23, 0x00FF00FFu);
+        const unsigned o2 = __viaddmin_s16x2_relu(od, d23, 0x00FF00FFu);
+        out.y = __byte_perm(e2, o2, 0x6240);
+    }
+    return out;
+}
+
+// Generic path: any dtype / stride / alignment.
+template <typename T>
+__device__ __forceinline__ void load_tile_generic(const uint8_t* p, unsigned pitch, int es, float (&S)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T* r0 = reinterpret_cast<const T*>(row_ptr(p, 2 * i, pitch));
+        const T* r1 = reinterpret_cast<const T*>(row_ptr(p, 2 * i + 1, pitch));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = (float)r0[(2 * j) * es], b = (float)r0[(2 * j + 1) * es];
+            const float c = (float)r1[(2 * j) * es], d = (float)r1[(2 * j + 1) * es];
+            S[4 * i + j] = (a + b) + (c + d);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-block quantisation
+// ------------------------------------------------------------------------------------------
+// Per-sample increment of each 2x2 of the tile for watermark bit `bit`: D[4*i+j] = (S'-S)[i][j]/4.
+// kStash: park S in shared memory while the eigen-iteration runs (4 STS.128 + 4 LDS.128 per
+// thread) instead of letting the compiler rebuild it from the pixel bytes under register pressure.
+template <bool kStash>
+__device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scale, float inv_scale,
+                                             float bias, float (&D)[16], float4* stash) {
+    float v[4];
+    bool zero;
+    if (kStash) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)   // asm: the compiler must not forward these stores to the loads below
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)),
+                         "f"(S[4 * i]), "f"(S[4 * i + 1]), "f"(S[4 * i + 2]), "f"(S[4 * i + 3]) : "memory");
+    }
+    const float sigma = 0.5f * top_singular<true>(S, v, zero);   // sigma_0 of the LL block
+    float q, rem;
+    floor_divmod(sigma, scale, inv_scale, q, rem);
+    const float target = (q + 0.25f + 0.5f * (float)bit) * scale;
+    if (zero) {
+        // svd(0) = (I, 0, I): the reference puts sigma_0' on DCT coefficient [0][0], i.e. a flat
+        // block target/4 in the LL band -> target/8 on every sample.
+#pragma unroll
+        for (int k = 0; k < 16; ++k) D[k] = fmaf(target, 0.125f, bias);
+        return;
+    }
+    const float t = 0.25f * ((target - sigma) / sigma);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float s0 = S[4 * i], s1 = S[4 * i + 1], s2 = S[4 * i + 2], s3 = S[4 * i + 3];
+        if (kStash) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s0), "=f"(s1), "=f"(s2), "=f"(s3)
+                         : "r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)) : "memory");
+        }
+        const float sv = fmaf(s3, v[3], fmaf(s2, v[2], fmaf(s1, v[1], s0 * v[0])));
+        const float a = t * sv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) D[4 * i + j] = fmaf(a, v[j], bias);
+    }
+}
+
+__device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, float inv_scale, float& sigma) {
+    float v[4];
+    bool zero;
+    sigma = 0.5f * top_singular<false>(S, v, zero);
+    float q, rem;
+    floor_divmod(sigma, scale, inv_scale, q, rem);
+    return rem > 0.5f * scale ? 1 : 0;
+}
+
+
+}  // namespace b200wm

@@ -1,0 +1,353 @@
+// TMA-staged, persistent variants of the Haar-DWT / block-SVD embed and extract kernels (sm_100a).
+//
+// Same arithmetic and outputs as dwtsvd.cu (the per-tile functions are shared through
+// dwtsvd_tile.cuh); what changes is how the frame strips travel:
+//
+//   * A work item is one STRIP: the 8 sample rows of one tile row of one frame.  With tight rows
+//     (pitch == width) a strip is 8*width contiguous bytes (15 KB at 1080p, 30 KB at 4K), so it
+//     moves with ONE bulk-copy TMA instruction (cp.async.bulk, SASS UBLKCP) instead of one
+//     vector load per thread and row.  (A first version used 2-D tensor-map boxes of 256x8
+//     bytes per warp; ncu showed the copy engine saturating on those small boxes at 2.3 TB/s -
+//     profiles/r01_summary.md - which is why the strips are now whole rows.)
+//   * Each CTA is persistent and owns a ring of kStages strip buffers in shared memory.  One
+//     elected thread issues the bulk loads for the strips the CTA will need next and arms an
+//     mbarrier with the byte count; all threads wait on the barrier's phase.  HBM latency is
+//     hidden by the ring depth, no thread spends issue slots on global address arithmetic and
+//     the 64 source bytes of a tile never occupy registers for the length of the SVD.
+//   * Thread t owns tile t of the strip: it reads its 8x8 bytes from shared memory
+//     (conflict-free: a warp reads 256 contiguous bytes per row).  Embed updates the strip in
+//     shared memory and writes it back with a bulk store (cp.async.bulk ... bulk_group); a slot
+//     is refilled one iteration after its store was committed
+//     (cp.async.bulk.wait_group.read 1), so loads, math and stores of neighbouring strips
+//     overlap.
+//   * Strips are aligned to tile rows, not to the 32-bit words of the packed bit arrays, so the
+//     extract kernel ORs each warp's ballot into (at most two) words of a zeroed raw-bit array
+//     and the embed kernel funnel-shifts its 32 watermark bits out of two words.
+//
+// Requirements (otherwise the launcher uses the vectorised-load kernels): planar uint8 with
+// tight rows (pitch == width), width a multiple of 16, base and frame stride multiples of 16
+// bytes, at least 64 tiles per row, and three strips fitting in shared memory.
+#include "common.cuh"
+#include "svd4.cuh"
+#include "dwtsvd_tile.cuh"
+
+namespace b200wm {
+
+constexpr int kStripThreads = 256;
+constexpr int kStages = 3;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "B200WM_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra B200WM_DONE;\n"
+        "bra B200WM_WAIT;\n"
+        "B200WM_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0, 16-byte aligned)
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// shared -> global bulk copy, tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint2 lds_u2(unsigned addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts_u2(unsigned addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// ---- work items ---------------------------------------------------------------------------------------
+struct Item {
+    int frame, ty;
+};
+
+struct StripGeom {
+    TileGeom g;
+    int n_frames;
+    int step_frames, step_ty;        // grid size split into whole frames and tile rows
+    unsigned pitch;                  // == width
+    unsigned strip_bytes;            // 8 * pitch
+    long long frame_stride;
+};
+
+__device__ __forceinline__ void advance(Item& it, const StripGeom& sg) {
+    it.frame += sg.step_frames;
+    it.ty += sg.step_ty;
+    if (it.ty >= sg.g.tiles_y) { it.ty -= sg.g.tiles_y; ++it.frame; }
+}
+
+__device__ __forceinline__ long long strip_offset(const Item& it, const StripGeom& sg) {
+    return it.frame * sg.frame_stride + (long long)it.ty * sg.strip_bytes;
+}
+
+__device__ __forceinline__ void init_ring(unsigned bar0) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// ---- extract -------------------------------------------------------------------------------------------
+// raw_bits must be zero on entry (the launcher clears it): warps OR their bits in.
+__global__ void __launch_bounds__(kStripThreads) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src, ExtractArgs ex,
+                                                                          StripGeom sg) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long bars[kStages];
+    __shared__ int cta_counts[2][32];        // per-strip vote counts, double-buffered by iteration parity
+    const unsigned ring = smem_u32(smem);
+    const unsigned bar0 = smem_u32(&bars[0]);
+    const int lane = threadIdx.x & 31;
+    const TileGeom& g = sg.g;
+    if (threadIdx.x < 64) cta_counts[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+    init_ring(bar0);
+
+    Item it{(int)blockIdx.x / g.tiles_y, (int)blockIdx.x % g.tiles_y};
+    if (threadIdx.x == 0) {          // prologue: fill the ring
+        Item p = it;
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            if (p.frame < sg.n_frames) {
+                mbar_arrive_expect_tx(bar0 + 8 * s, sg.strip_bytes);
+                bulk_load(ring + s * sg.strip_bytes, src + strip_offset(p, sg), sg.strip_bytes, bar0 + 8 * s);
+            }
+            advance(p, sg);
+        }
+    }
+    Item ahead = it;                 // the strip kStages iterations ahead (what a freed slot is refilled with)
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) advance(ahead, sg);
+
+    int stage = 0, flip = 0;
+    unsigned parity = 0;
+    const int L = ex.payload_len;
+    for (; it.frame < sg.n_frames; advance(it, sg), advance(ahead, sg), flip ^= 1) {
+        const unsigned slot = ring + stage * sg.strip_bytes;
+        mbar_wait(bar0 + 8 * stage, parity);
+        for (int t0 = 0; t0 < g.tiles_x; t0 += kStripThreads) {      // one pass at 1080p, two at 4K
+            const int t = t0 + threadIdx.x;
+            const bool live = t < g.tiles_x;
+            int bit = 0;
+            if (live) {
+                float S[16];
+                {
+                    uint2 rows[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) rows[r] = lds_u2(slot + r * sg.pitch + t * 8);
+                    sums_from_rows(rows, S);
+                }
+                float sigma;
+                bit = extract_bit(S, ex.scale, ex.inv_scale, sigma);
+            }
+            if (t0 + (threadIdx.x & ~31) < g.tiles_x) {                 // warp-uniform: this warp holds tiles
+                const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
+                const unsigned c0 = (unsigned)(it.ty * g.tiles_x + t0 + (threadIdx.x & ~31));
+                const unsigned sh = c0 & 31u;
+                if (lane == 0 && ballot) {
+                    uint32_t* w = ex.raw_bits + (long long)it.frame * g.words + (c0 >> 5);
+                    atomicOr(w, ballot << sh);
+                    if (sh && (ballot >> (32u - sh))) atomicOr(w + 1, ballot >> (32u - sh));
+                }
+                if (ex.pos_counts && lane < L) {
+                    // lane i sees the bits of blocks c0+i, c0+i+L, ...: payload position (c0 + i) mod L
+                    const int n = __popc(ballot & (ex.every << lane));
+                    if (n) atomicAdd(&cta_counts[flip][(c0 + lane) & (unsigned)(L - 1)], n);
+                }
+            }
+        }
+        __syncthreads();             // every thread has consumed its bytes: the slot may be overwritten
+        if (ex.pos_counts && (int)threadIdx.x < L) {
+            // one global update per position and strip; this buffer is next touched two barriers from now
+            const int n = cta_counts[flip][threadIdx.x];
+            if (n) {
+                atomicAdd(&ex.pos_counts[(long long)it.frame * L + threadIdx.x], n);
+                cta_counts[flip][threadIdx.x] = 0;
+            }
+        }
+        if (threadIdx.x == 0 && ahead.frame < sg.n_frames) {
+            mbar_arrive_expect_tx(bar0 + 8 * stage, sg.strip_bytes);
+            bulk_load(slot, src + strip_offset(ahead, sg), sg.strip_bytes, bar0 + 8 * stage);
+        }
+        if (++stage == kStages) { stage = 0; parity ^= 1u; }
+    }
+}
+
+// ---- embed ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                        EmbedArgs em, StripGeom sg) {
+    static_assert(kStages >= 3, "a slot is refilled one iteration after its store was committed");
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long bars[kStages];
+    const unsigned ring = smem_u32(smem);
+    const unsigned bar0 = smem_u32(&bars[0]);
+    const int lane = threadIdx.x & 31;
+    const TileGeom& g = sg.g;
+    init_ring(bar0);
+
+    Item it{(int)blockIdx.x / g.tiles_y, (int)blockIdx.x % g.tiles_y};
+    if (threadIdx.x == 0) {
+        Item p = it;
+#pragma unroll
+        for (int s = 0; s < kStages - 1; ++s) {          // the last slot is filled by the first refill
+            if (p.frame < sg.n_frames) {
+                mbar_arrive_expect_tx(bar0 + 8 * s, sg.strip_bytes);
+                bulk_load(ring + s * sg.strip_bytes, src + strip_offset(p, sg), sg.strip_bytes, bar0 + 8 * s);
+            }
+            advance(p, sg);
+        }
+    }
+    Item ahead = it;                 // the strip kStages-1 iterations ahead
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) advance(ahead, sg);
+
+    int stage = 0, refill = kStages - 1;
+    unsigned parity = 0;
+    for (; it.frame < sg.n_frames; advance(it, sg), advance(ahead, sg)) {
+        const unsigned slot = ring + stage * sg.strip_bytes;
+        // the 32 watermark bits of each warp's tiles, funnel-shifted out of two words of the packed
+        // row; issued before the wait so that their latency hides behind it
+        const int row = em.frame_row ? em.frame_row[it.frame] : 0;
+        const uint32_t* wrow = em.wm + (long long)row * em.wm_words;
+        auto warp_bits = [&](int t0) -> unsigned {
+            const unsigned c0 = (unsigned)(it.ty * g.tiles_x + t0 + (threadIdx.x & ~31));
+            const int wi = (int)(c0 >> 5);
+            if (wi >= em.wm_words) return 0u;
+            const unsigned lo = wrow[wi], hi = (wi + 1 < em.wm_words) ? wrow[wi + 1] : 0u;
+            return __funnelshift_r(lo, hi, c0 & 31u);
+        };
+        unsigned bits = warp_bits(0);
+        mbar_wait(bar0 + 8 * stage, parity);
+        for (int t0 = 0; t0 < g.tiles_x; t0 += kStripThreads) {
+            const int t = t0 + threadIdx.x;
+            if (t0 > 0) bits = warp_bits(t0);
+            if (t < g.tiles_x) {
+                const unsigned mine = slot + t * 8;
+                float S[16], D[16];
+                {
+                    uint2 rows[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) rows[r] = lds_u2(mine + r * sg.pitch);
+                    sums_from_rows(rows, S);
+                }
+                embed_deltas<false>(S, (bits >> lane) & 1u, em.scale, em.inv_scale, 12582912.0f, D, nullptr);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned d01 = __byte_perm(__float_as_uint(D[4 * i + 0]), __float_as_uint(D[4 * i + 1]), 0x5410);
+                    const unsigned d23 = __byte_perm(__float_as_uint(D[4 * i + 2]), __float_as_uint(D[4 * i + 3]), 0x5410);
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const unsigned a = mine + (2 * i + rr) * sg.pitch;
+                        sts_u2(a, add_clamp_row(lds_u2(a), d01, d23));
+                    }
+                }
+            }
+        }
+        fence_async_smem();          // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store(dst + strip_offset(it, sg), slot, sg.strip_bytes);
+            bulk_commit();
+            // the slot stored one iteration ago has been read by now (at most this store pending)
+            bulk_wait_read<1>();
+            if (ahead.frame < sg.n_frames) {
+                mbar_arrive_expect_tx(bar0 + 8 * refill, sg.strip_bytes);
+                bulk_load(ring + refill * sg.strip_bytes, src + strip_offset(ahead, sg), sg.strip_bytes, bar0 + 8 * refill);
+            }
+        }
+        refill = stage;
+        if (++stage == kStages) { stage = 0; parity ^= 1u; }
+    }
+    if (threadIdx.x == 0) bulk_wait_read<0>();
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+constexpr size_t kMaxRingBytes = 200 * 1024;
+
+bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const TileGeom& g) {
+    return pl->dtype == B200WM_U8 && pl->elem_stride == 1 && pl->pitch_bytes == pl->width && (pl->width % 16) == 0 &&
+           ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && (pl->frame_stride_bytes % 16) == 0 &&
+           (pl->n_frames <= 1 || pl->frame_stride_bytes >= pl->pitch_bytes * (long long)pl->height) && g.tiles_x >= 64 &&
+           g.tiles_y > 0 && (size_t)kStages * 8 * (size_t)pl->pitch_bytes <= kMaxRingBytes &&
+           (long long)pl->n_frames * g.tiles_y < (1ll << 31);
+}
+
+template <typename Kernel>
+static int persistent_grid(Kernel kernel, size_t smem, int* blocks) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        B200WM_CUDA_TRY(cudaGetDevice(&dev));
+        B200WM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    B200WM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B200WM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStripThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    *blocks = sms * per_sm;
+    return B200WM_OK;
+}
+
+static StripGeom make_strip_geom(const TileGeom& g, const b200wm_plane* pl, int blocks) {
+    StripGeom sg;
+    sg.g = g;
+    sg.n_frames = pl->n_frames;
+    sg.step_frames = blocks / g.tiles_y;
+    sg.step_ty = blocks % g.tiles_y;
+    sg.pitch = (unsigned)pl->pitch_bytes;
+    sg.strip_bytes = 8u * sg.pitch;
+    sg.frame_stride = pl->frame_stride_bytes;
+    return sg;
+}
+
+int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const TileGeom& g, ExtractArgs xa, cudaStream_t stream) {
+    const size_t smem = (size_t)kStages * 8 * (size_t)pl->pitch_bytes;
+    int blocks = 0;
+    int rc = persistent_grid(dwtsvd_extract_tma_kernel, smem, &blocks);
+    if (rc) return rc;
+    const long long strips = (long long)pl->n_frames * g.tiles_y;
+    if (strips < blocks) blocks = (int)strips;
+    dwtsvd_extract_tma_kernel<<<blocks, kStripThreads, smem, stream>>>((const uint8_t*)src, xa, make_strip_geom(g, pl, blocks));
+    B200WM_LAUNCH_CHECK("dwtsvd_extract_tma_kernel");
+    return B200WM_OK;
+}
+
+int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, const TileGeom& g, EmbedArgs ea,
+                            cudaStream_t stream) {
+    const size_t smem = (size_t)kStages * 8 * (size_t)pl->pitch_bytes;
+    int blocks = 0;
+    int rc = persistent_grid(dwtsvd_embed_tma_kernel, smem, &blocks);
+    if (rc) return rc;
+    const long long strips = (long long)pl->n_frames * g.tiles_y;
+    if (strips < blocks) blocks = (int)strips;
+    dwtsvd_embed_tma_kernel<<<blocks, kStripThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea,
+                                                                     make_strip_geom(g, pl, blocks));
+    B200WM_LAUNCH_CHECK("dwtsvd_embed_tma_kernel");
+    return B200WM_OK;
+}
+
+}  // namespace b200wm

@@ -16,6 +16,7 @@
 // (2 lambda <= tr) or converge slowly fall back to a cyclic Jacobi eigen-solver in fp64.
 #pragma once
 #include <cuda_runtime.h>
+#include "common.cuh"
 
 namespace b200wm {
 
@@ -55,7 +56,7 @@ __device__ __forceinline__ float dot4(const float (&a)[4], const float (&b)[4]) 
 // footprint of the kernels that call it once in a few thousand blocks.
 struct Top5 { float v0, v1, v2, v3, sigma; };
 
-__device__ __noinline__ Top5 top_pair_jacobi(float s0, float s1, float s2, float s3, float s4, float s5, float s6, float s7,
+static __device__ __noinline__ Top5 top_pair_jacobi(float s0, float s1, float s2, float s3, float s4, float s5, float s6, float s7,
                                              float s8, float s9, float s10, float s11, float s12, float s13, float s14,
                                              float s15) {
     // arguments arrive by value so that the caller's block never has its address taken
@@ -146,11 +147,7 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
     float G[10];
     gram4(S, G);
     const float tr_raw = (G[0] + G[4]) + (G[7] + G[9]);
-    zero_block = !(tr_raw > 0.0f);
-    if (zero_block) {
-        v[0] = v[1] = v[2] = v[3] = 0.0f;
-        return 0.0f;
-    }
+    zero_block = !(tr_raw > 0.0f);           // handled with selects at the end: no early exit
     // Exact power-of-two normalisation: tr = tr_raw * 2^-(e+1) lies in [0.5, 1), so the iterates
     // need no rescaling and nothing is rounded (G stays exact for uint8 input).
     const unsigned ebits = __float_as_uint(tr_raw) & 0x7F800000u;
@@ -168,7 +165,7 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
     symv4(G, w, x);                              // second power step, unchecked: one step alone almost never certifies
     symv4(G, x, w);
     float xw, xx;
-    bool done = rayleigh_check(x, w, tr, xw, xx);
+    bool done = rayleigh_check(x, w, tr, xw, xx) || zero_block;
     if (!done) {
 #pragma unroll 1
         for (int it = 0; it < kPowerIters && !done; ++it) {
@@ -179,13 +176,13 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
         }
     }
     if (done) {
-        const float lam = (xw / xx) * up;          // IEEE division: this is the result
+        const float lam = div_pos(xw, xx) * up;
         if (kWantVec) {
-            const float n = rsqrtf(xx);
+            const float n = zero_block ? 0.0f : rsqrtf(xx);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = x[k] * n;
+            for (int k = 0; k < 4; ++k) v[k] = zero_block ? 0.0f : x[k] * n;
         }
-        return sqrtf(lam);
+        return zero_block ? 0.0f : sqrt_pos(lam);
     }
     const Top5 t = top_pair_jacobi(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8], S[9], S[10], S[11], S[12],
                                    S[13], S[14], S[15]);
