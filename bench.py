@@ -46,8 +46,8 @@ METRIC = "frames_per_sec_1080p_embed_extract"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--frames", type=int, default=3000, help="frames per GPU")
     p.add_argument("--e2e-frames", type=int, default=3000)
@@ -95,43 +95,87 @@ def segment_rows(first_segment, n_segments):
 
 # --------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in a thread, 5 ms period;
+    nvidia-smi as a fallback).  The device index is the physical one behind CUDA_VISIBLE_DEVICES."""
+
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, index):
-        self.samples, self.proc = [], None
+        self.samples, self.stop_flag, self.thread, self.nvml, self.smi = [], False, None, None, None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                index = int(vis.split(",")[index])
+            except (ValueError, IndexError):
+                pass
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nvml = None
+            self._start_smi(index)
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.samples.append((time.time(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _start_smi(self, index):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                         "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except OSError:
-            self.proc = None
+            self.smi = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [s for t, s in self.samples if t0 - 0.05 <= t <= t1 + 0.15] or [s for _, s in self.samples[-3:]]
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            parts = [x.strip() for x in r.split(",")]
+    def _read_smi(self):
+        for line in self.smi.stdout:
+            parts = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                mask = sum(1 << i for i, v in enumerate(parts[2:6]) if v.lower().startswith("active"))
+                self.samples.append((time.time(), float(parts[0]), mask, float(parts[1])))
             except (ValueError, IndexError):
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self, t0, t1):
+        self.stop_flag = True
+        if self.smi is not None:
+            time.sleep(0.06)
+            self.smi.terminate()
+        if self.nvml is None and self.smi is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        used = inside or self.samples[-2:]
+        reasons = set()
+        for s in used:
+            if self.nvml is not None:
+                for name, attr in self.REASONS:
+                    if s[2] & getattr(self.nvml, attr):
+                        reasons.add(name)
+            else:
+                for i, (name, _) in enumerate(self.REASONS):
+                    if s[2] & (1 << i):
+                        reasons.add(name)
+        max_mhz = self.max_mhz if self.nvml is not None else (max(s[3] for s in used) if used else None)
+        return {"sm_mhz": float(np.median([s[1] for s in used])) if used else None, "sm_max_mhz": max_mhz,
+                "reasons": sorted(reasons), "samples": len(inside), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------- CPU baseline (oracle port)
@@ -140,7 +184,7 @@ def _cpu_worker(args):
     from oracle import dwt_dct_svd as o_svd, payload as o_pay
     out = []
     for y in planes:
-        yuv = np.zeros((H, W, 3), dtype=np.float32)
+        yuv = np.zeros(y.shape + (3,), dtype=np.float32)
         yuv[:, :, 1] = y
         o_svd.encode_per_block(yuv, wm_row[None, :])
         yuv[:, :, 1] = np.around(np.clip(yuv[:, :, 1], 0, 255))
@@ -149,50 +193,72 @@ def _cpu_worker(args):
     return out
 
 
-def cpu_baseline(planes_host, wm_row, frames_per_core=1, cores=None):
-    """fps of the reference's per-block CPU path (oracle port) using every host core."""
+def cpu_baseline(planes_host, wm_row, frames_per_core=1, cores=None, band_rows=H, pool=None):
+    """fps of the reference's per-block CPU path (oracle port) using every host core.  Each core
+    gets ``frames_per_core`` bands of ``band_rows`` rows (a whole 1080p frame by default; blocks are
+    independent, so a band of whole tile rows is a valid bounded sample)."""
     import multiprocessing as mp
     for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[var] = "1"              # one process per core; inherited by the spawned workers
     cores = cores or os.cpu_count() or 1
+    band_rows = max(8, min(H, band_rows // 8 * 8))
     n = min(len(planes_host), cores * frames_per_core)
     cores = min(cores, n)
-    jobs = [(planes_host[i::cores][:frames_per_core], wm_row) for i in range(cores)]
+    jobs = [(planes_host[i::cores][:frames_per_core, :band_rows], wm_row) for i in range(cores)]
     n = sum(len(j[0]) for j in jobs)
-    with mp.get_context("spawn").Pool(cores) as pool:
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
         pool.map(_cpu_worker, [(p[:0], wm_row) for p, _ in jobs])        # start the workers, import numpy/cv2
+    try:
         t0 = time.perf_counter()
         pool.map(_cpu_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n} of the batch's 1080p frames, embed+extract+per-frame vote, oracle per-block port "
-                      f"(cv2.dct + np.linalg.svd per 4x4 block, like the reference), {cores} processes, {dt:.1f} s"}
+    finally:
+        if own:
+            pool.close()
+    frames = n * band_rows / H
+    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port", "seconds": dt,
+            "sample": f"{n} bands of {band_rows}x{W} ({frames:.2f} 1080p frames) of the batch, embed+extract+per-frame vote, "
+                      f"oracle per-block port (cv2.dct + np.linalg.svd per 4x4 block, like the reference), "
+                      f"{cores} processes, {dt:.1f} s"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     from offmark_b200.generator.shuffler import Shuffler
     from oracle import synth
     cores = os.cpu_count() or 1
-    n = cores * args.cpu_frames_per_core
-    distinct = [synth.luma_plane_u8(H, W, f, SEED) for f in range(min(n, 8))]
-    planes = np.stack([distinct[i % len(distinct)] for i in range(n)])
+    distinct = [synth.luma_plane_u8(H, W, f, SEED) for f in range(min(cores, 8))]
+    planes = np.stack([distinct[i % len(distinct)] for i in range(cores)])
     wm_row = Shuffler(key=KEY).generate_wm(np.array([0, 1, 1, 0, 0, 1, 0, 1]), (1, H * W // 64))[0]
-    times = []
-    res = None
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    pool = mp.get_context("spawn").Pool(cores)
+    pool.map(_cpu_worker, [(planes[:0], wm_row)] * cores)
+    # size the per-step sample so that the whole run stays near two minutes: one core needs about
+    # 2 s per 1080p frame, i.e. ~15 ms per tile row
+    probe = cpu_baseline(planes, wm_row, 1, cores, band_rows=64, pool=pool)
+    sec_per_row = probe["seconds"] / 64
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    band_rows = int(max(8, min(H, budget / sec_per_row)))
+    results = []
     for step in range(args.warmup + args.steps):
-        res = cpu_baseline(planes, wm_row, args.cpu_frames_per_core, cores)
+        res = cpu_baseline(planes, wm_row, 1, cores, band_rows=band_rows, pool=pool)
         if step >= args.warmup:
-            times.append(res)
-    fps = float(np.mean([r["value"] for r in times])) if times else res["value"]
-    frames = cores * args.cpu_frames_per_core
+            results.append(res)
+    pool.close()
+    fps = float(np.mean([r["value"] for r in results]))
+    last = results[-1]
+    frames = cores * (max(8, band_rows // 8 * 8)) / H
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * frames / fps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, frames),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+            "config": workload_config(args, args.frames),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -267,10 +333,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step(False)
     fence()
-    sampler = ClockSampler(local_rank)
     launches0 = ops.kernel_launches()
     t_wall0 = time.time()
     start, stop = ev(), ev()
