@@ -209,6 +209,34 @@ B200WM_API int b200wm_pattern_hist(const uint64_t* packed, const int32_t* frame_
 B200WM_API int b200wm_bgr8_to_yuv32(const uint8_t* bgr, float* yuv, int64_t n_pixels, void* stream);
 B200WM_API int b200wm_yuv32_to_bgr8(const float* yuv, uint8_t* bgr, int64_t n_pixels, void* stream);
 
+/* ---- colour bracket fused with the DWT/SVD pair -------------------------- */
+/*
+ * Embedder.__mark_frame (video/embedder.py:33-39) in one kernel: uint8 H x W x 3 frames as FileDecoder
+ * yields them (video/frame_reader.py:59-63) -> float YUV (OpenCV BGR2YUV float formulas) -> DWT/SVD
+ * embed on every channel c with scales[c] > 0 (host array of 3 floats; the reference default is
+ * {0, 15, 0}) -> YUV2BGR -> clip -> round-half-even -> uint8.  dst may equal src.
+ */
+B200WM_API int b200wm_dwtsvd_embed_rgb8(const uint8_t* src, uint8_t* dst, int32_t n_frames, int32_t height, int32_t width,
+                            int64_t pitch_bytes, int64_t frame_stride_bytes, const float* scales, const uint32_t* wm_packed,
+                            int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, void* stream);
+/*
+ * Extractor.__check_frame's conversion + DwtDctSvdDecoder.decode on YUV channel `channel`
+ * (video/extractor.py:30-33, extract/dwt_dct_svd_decoder.py:12-37) in one kernel.  Outputs as
+ * b200wm_dwtsvd_extract.
+ */
+B200WM_API int b200wm_dwtsvd_extract_rgb8(const uint8_t* src, int32_t n_frames, int32_t height, int32_t width, int64_t pitch_bytes,
+                              int64_t frame_stride_bytes, int32_t channel, float scale, uint32_t* raw_bits,
+                              int32_t words_per_frame, int32_t payload_len, int32_t* pos_counts, void* stream);
+
+/* ---- distortion channel for robustness studies (no counterpart in the reference) ---- */
+/*
+ * JPEG-like requantisation of planar uint8 planes: per 8x8 block DCT(x-128), quantise and dequantise
+ * with the libjpeg luminance table scaled to `quality` (1..100), IDCT, round, clip.  dst may equal src.
+ */
+B200WM_API int b200wm_attack_jpeg_requant(const void* src, void* dst, const b200wm_plane* plane, int32_t quality, void* stream);
+/* x + noise (float32 [n_frames, height, width], contiguous), round, clip.  dst may equal src. */
+B200WM_API int b200wm_attack_add_noise(const void* src, void* dst, const b200wm_plane* plane, const float* noise, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

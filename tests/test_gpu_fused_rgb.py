@@ -1,0 +1,80 @@
+"""GPU: colour bracket fused into the DWT/SVD kernels vs the reference flow
+(video/embedder.py:33-39 + embed/dwt_dct_svd_encoder.py, video/extractor.py:30-34 + decoder)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bracket, dwt_dct_svd as o_svd, payload as o_pay, synth
+from parity import PAYLOAD, KEY, knife_edge_blocks, tile_mask_to_pixels
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _frames(golden_dir):
+    g = np.load(os.path.join(golden_dir, "in_mp4_frames.npz"))
+    yield "in.mp4[0]", g["rgb_0"], (g["rgb_0"].astype(np.int16) + g["marked_minus_src_0"]).astype(np.uint8)
+    yield "frame63 crop", np.load(os.path.join(golden_dir, "frame63_crop.npz"))["bgr"], None
+    yield "synthetic 100x132", synth.random_bgr(100, 132, 9), None
+    yield "synthetic 37x53 (unaligned rows)", synth.random_bgr(37, 53, 10), None
+
+
+def test_fused_embed_matches_reference_flow(golden_dir):
+    from b200wm import ops
+    for name, frame, golden_marked in _frames(golden_dir):
+        h, w, _ = frame.shape
+        wm = o_pay.generate_wm(PAYLOAD, (1, h * w // 64), KEY)
+        want = bracket.mark_frame(frame, lambda y: o_svd.encode(y, wm))
+        if golden_marked is not None:
+            assert np.array_equal(want, golden_marked)           # the oracle flow IS the reference's output
+        t = torch.from_numpy(frame.copy()).to(DEV)
+        packed, n = ops.pack_bits(wm[0], device=DEV)
+        ops.dwtsvd_embed_rgb8_(t, packed, n)
+        got = t.cpu().numpy()
+        _, edge_floor, _ = knife_edge_blocks(bracket.to_yuv(frame)[:, :, 1])
+        ok = ~tile_mask_to_pixels(edge_floor, (h, w))
+        d = np.abs(got.astype(np.int16) - want).max(axis=2)
+        assert d[ok].max() <= 1, (name, d[ok].max())
+        assert (d > 0).mean() < 5e-3, (name, (d > 0).mean())
+        nr, nc = o_svd.block_grid(h, w)
+        assert np.array_equal(got[nr * 8:], frame[nr * 8:]) and np.array_equal(got[:, nc * 8:], frame[:, nc * 8:])
+        # both extractors read the payload back from the fused output
+        bits_ref = o_svd.decode(bracket.to_yuv(got))
+        raw, counts = ops.dwtsvd_extract_rgb8(torch.from_numpy(got).to(DEV), payload_len=8)
+        bits = ops.unpack_bits(raw, bits_ref.size)
+        diff = np.flatnonzero(bits[0] != bits_ref[0])
+        edge, _, _ = knife_edge_blocks(bracket.to_yuv(got)[:, :, 1])
+        assert all(c < edge.size and edge[c] for c in diff), name
+        if nr * nc >= 64:
+            assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), PAYLOAD), name
+        assert counts[0].cpu().tolist() == [int(bits[0][i::8].sum()) for i in range(8)]
+
+
+def test_fused_path_equals_three_kernel_path():
+    """mark_rgb8 == bgr8_to_yuv32 -> dwtsvd_embed -> yuv32_to_bgr8 up to the last-bit ties of the rounding."""
+    from b200wm import ops
+    frame = synth.random_bgr(240, 320, 3)
+    wm = o_pay.generate_wm(PAYLOAD, (1, 240 * 320 // 64), KEY)
+    packed, n = ops.pack_bits(wm[0], device=DEV)
+    a = torch.from_numpy(frame.copy()).to(DEV)
+    ops.dwtsvd_embed_rgb8_(a, packed, n)
+    yuv = ops.bgr8_to_yuv32(torch.from_numpy(frame).to(DEV))
+    ops.dwtsvd_embed_(yuv, packed, n, channel=1)
+    b = ops.yuv32_to_bgr8(yuv)
+    d = (a.int() - b.int()).abs()
+    assert d.max().item() <= 1 and (d > 0).float().mean().item() < 1e-3
+
+
+def test_batched_frames_and_scales():
+    from b200wm import ops
+    frames = np.stack([synth.random_bgr(64, 96, s) for s in range(3)])
+    wm = o_pay.generate_wm(PAYLOAD, (1, 64 * 96 // 64), KEY)
+    packed, n = ops.pack_bits(wm[0], device=DEV)
+    t = torch.from_numpy(frames.copy()).to(DEV)
+    ops.dwtsvd_embed_rgb8_(t, packed, n, scales=(20.0, 15.0, 0.0))      # mark Y and U
+    got = t.cpu().numpy()
+    for f in range(3):
+        want = bracket.mark_frame(frames[f], lambda y: o_svd.encode(y, wm, scales=(20, 15, 0)))
+        assert np.abs(got[f].astype(np.int16) - want).max() <= 1

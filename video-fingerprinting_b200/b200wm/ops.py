@@ -257,6 +257,59 @@ def yuv32_to_bgr8(yuv):
     return out
 
 
+# ----------------------------------------------------------------------------- fused colour bracket
+def _rgb_frames(frames):
+    if not isinstance(frames, torch.Tensor) or not frames.is_cuda or frames.dtype != torch.uint8:
+        raise ValueError("frames must be a CUDA uint8 tensor")
+    f = frames.unsqueeze(0) if frames.dim() == 3 else frames
+    if f.dim() != 4 or f.shape[3] != 3 or f.stride(3) != 1 or f.stride(2) != 3:
+        raise ValueError("frames must be [N, H, W, 3] (or [H, W, 3]) with packed pixels")
+    n, h, w, _ = f.shape
+    return f, n, h, w, f.stride(1), (f.stride(0) if n > 1 else 0)
+
+
+def dwtsvd_embed_rgb8_(frames, wm_packed, wm_len, scales=(0.0, 15.0, 0.0), frame_wm_row=None):
+    """uint8 [N, H, W, 3] frames marked in place: colour conversion, DWT/SVD embed on the channels
+    with a positive scale and conversion back, in one kernel (video/embedder.py:33-39)."""
+    require_cuda()
+    f, n, h, w, pitch, fstride = _rgb_frames(frames)
+    sc = (C.c_float * 3)(*[float(s) for s in scales])
+    check(lib.b200wm_dwtsvd_embed_rgb8(_ptr(f), _ptr(f), n, h, w, pitch, fstride, sc, _ptr(wm_packed), wm_packed.shape[1],
+                                       int(wm_len), _ptr(frame_wm_row), _stream()))
+    return frames
+
+
+def dwtsvd_extract_rgb8(frames, scale=15.0, channel=1, payload_len=None):
+    """uint8 [N, H, W, 3] frames -> (raw_bits, pos_counts) of YUV channel ``channel`` (video/extractor.py:30-33)."""
+    require_cuda()
+    f, n, h, w, pitch, fstride = _rgb_frames(frames)
+    _, _, words = geometry(h, w)
+    raw_bits = _empty((n, words), torch.int32, f.device)
+    pos_counts = torch.empty((n, payload_len), dtype=torch.int32, device=f.device) if payload_len is not None else None
+    check(lib.b200wm_dwtsvd_extract_rgb8(_ptr(f), n, h, w, pitch, fstride, int(channel), float(scale), _ptr(raw_bits), words,
+                                         int(payload_len or 0), _ptr(pos_counts), _stream()))
+    return raw_bits, pos_counts
+
+
+# ----------------------------------------------------------------------------- distortion channel
+def attack_jpeg_requant_(planes, quality):
+    """In-place JPEG-like requantisation of planar uint8 planes (BASELINE config 5)."""
+    require_cuda()
+    v, pl = describe(planes)
+    check(lib.b200wm_attack_jpeg_requant(_ptr(v), _ptr(v), C.byref(pl), int(quality), _stream()))
+    return planes
+
+
+def attack_add_noise_(planes, noise):
+    """In-place ``clip(round(x + noise))``; ``noise`` float32 ``[N, H, W]`` contiguous on the same device."""
+    require_cuda()
+    v, pl = describe(planes)
+    if noise.dtype != torch.float32 or not noise.is_contiguous() or noise.numel() != v.numel():
+        raise ValueError("noise must be a contiguous float32 tensor with one value per sample")
+    check(lib.b200wm_attack_add_noise(_ptr(v), _ptr(v), C.byref(pl), _ptr(noise), _stream()))
+    return planes
+
+
 def set_path(path):
     """0 = automatic (TMA-staged kernels when the planes qualify), 1 = vectorised-load kernels only."""
     check(lib.b200wm_set_path(int(path)))

@@ -27,6 +27,11 @@ int launch_dct8_embed(const void*, void*, const b200wm_plane*, const float*, con
 int launch_dct8_extract(const void*, const b200wm_plane*, const float*, const float*, const double*, float, uint32_t*, int,
                         int, int32_t*, cudaStream_t);
 int launch_bgr8_to_yuv32(const uint8_t*, float*, long long, cudaStream_t);
+int launch_attack_jpeg(const void*, void*, const b200wm_plane*, int, cudaStream_t);
+int launch_attack_noise(const void*, void*, const b200wm_plane*, const float*, cudaStream_t);
+int launch_embed_rgb8(const uint8_t*, uint8_t*, int, int, int, long long, long long, const float*, const uint32_t*, int, long long,
+                      const int32_t*, cudaStream_t);
+int launch_extract_rgb8(const uint8_t*, int, int, int, long long, long long, int, float, uint32_t*, int, int, int32_t*, cudaStream_t);
 void set_path(int);
 int get_path();
 int launch_yuv32_to_bgr8(const float*, uint8_t*, long long, cudaStream_t);
@@ -147,6 +152,28 @@ B200WM_API int b200wm_bgr8_to_yuv32(const uint8_t* bgr, float* yuv, int64_t n_pi
 
 B200WM_API int b200wm_yuv32_to_bgr8(const float* yuv, uint8_t* bgr, int64_t n_pixels, void* stream) {
     return launch_yuv32_to_bgr8(yuv, bgr, n_pixels, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_attack_jpeg_requant(const void* src, void* dst, const b200wm_plane* plane, int32_t quality, void* stream) {
+    return launch_attack_jpeg(src, dst, plane, quality, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_attack_add_noise(const void* src, void* dst, const b200wm_plane* plane, const float* noise, void* stream) {
+    return launch_attack_noise(src, dst, plane, noise, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_dwtsvd_embed_rgb8(const uint8_t* src, uint8_t* dst, int32_t n_frames, int32_t height, int32_t width,
+                            int64_t pitch_bytes, int64_t frame_stride_bytes, const float* scales, const uint32_t* wm_packed,
+                            int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, void* stream) {
+    return launch_embed_rgb8(src, dst, n_frames, height, width, pitch_bytes, frame_stride_bytes, scales, wm_packed, wm_words,
+                             wm_len, frame_wm_row, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_dwtsvd_extract_rgb8(const uint8_t* src, int32_t n_frames, int32_t height, int32_t width, int64_t pitch_bytes,
+                              int64_t frame_stride_bytes, int32_t channel, float scale, uint32_t* raw_bits,
+                              int32_t words_per_frame, int32_t payload_len, int32_t* pos_counts, void* stream) {
+    return launch_extract_rgb8(src, n_frames, height, width, pitch_bytes, frame_stride_bytes, channel, scale, raw_bits,
+                               words_per_frame, payload_len, pos_counts, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -16,35 +16,11 @@
 // so masks are a separate pass that also accumulates that sum per frame; embed/extract read
 // the per-block mean, texture mask and the frame sum (12 bytes per 64 samples).
 #include "common.cuh"
+#include "dct8.cuh"
 
 namespace b200wm {
 
 constexpr int kDctThreads = 128;
-
-// cos(k*pi/16), and the orthonormal scale factors
-#define C1 0.98078528040323043f
-#define C2 0.92387953251128674f
-#define C3 0.83146961230254524f
-#define C4 0.70710678118654752f
-#define C5 0.55557023301960218f
-#define C6 0.38268343236508977f
-#define C7 0.19509032201612825f
-
-// Orthonormal 8-point DCT-II in place: X_k = a_k sum_n x_n cos((2n+1) k pi / 16), a_0 = 1/sqrt(8), a_k = 1/2.
-__device__ __forceinline__ void dct8_1d(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
-                                        float& x7) {
-    const float s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
-    const float d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
-    const float e0 = s0 + s3, e1 = s1 + s2, e2 = s1 - s2, e3 = s0 - s3;
-    x0 = (e0 + e1) * (0.5f * C4);
-    x4 = (e0 - e1) * (0.5f * C4);
-    x2 = fmaf(e3, 0.5f * C2, e2 * (0.5f * C6));
-    x6 = fmaf(e3, 0.5f * C6, e2 * (-0.5f * C2));
-    x1 = fmaf(d3, 0.5f * C7, fmaf(d2, 0.5f * C5, fmaf(d1, 0.5f * C3, d0 * (0.5f * C1))));
-    x3 = fmaf(d3, -0.5f * C5, fmaf(d2, -0.5f * C1, fmaf(d1, -0.5f * C7, d0 * (0.5f * C3))));
-    x5 = fmaf(d3, 0.5f * C3, fmaf(d2, 0.5f * C7, fmaf(d1, -0.5f * C1, d0 * (0.5f * C5))));
-    x7 = fmaf(d3, -0.5f * C1, fmaf(d2, 0.5f * C3, fmaf(d1, -0.5f * C5, d0 * (0.5f * C7))));
-}
 
 template <typename T>
 __device__ __forceinline__ void load_block(const uint8_t* p, long long pitch, int es, float (&b)[64]) {
@@ -128,12 +104,7 @@ __global__ void __launch_bounds__(kDctThreads) dct8_masks_kernel(DctPlane pl, Bl
                            (long long)bx * 8 * pl.elem_stride * (long long)sizeof(T);
         float b[64];
         load_block<T>(p, pl.pitch, pl.elem_stride, b);
-#pragma unroll
-        for (int y = 0; y < 8; ++y)
-            dct8_1d(b[8 * y], b[8 * y + 1], b[8 * y + 2], b[8 * y + 3], b[8 * y + 4], b[8 * y + 5], b[8 * y + 6], b[8 * y + 7]);
-#pragma unroll
-        for (int x = 0; x < 8; ++x)
-            dct8_1d(b[x], b[8 + x], b[16 + x], b[24 + x], b[32 + x], b[40 + x], b[48 + x], b[56 + x]);
+        dct8x8(b);
         const float mean = b[0] * 0.125f;                  // mask[i][j] = coeffs[0][0]; mask /= 8
         const long long o = (long long)frame * g.nb + c;
         block_mean[o] = mean;

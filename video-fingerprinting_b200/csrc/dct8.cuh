@@ -1,0 +1,65 @@
+// Register-resident 8-point DCT-II / DCT-III butterflies (orthonormal, like cv2.dct / cv2.idct).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200wm {
+
+// cos(k*pi/16), and the orthonormal scale factors
+#define C1 0.98078528040323043f
+#define C2 0.92387953251128674f
+#define C3 0.83146961230254524f
+#define C4 0.70710678118654752f
+#define C5 0.55557023301960218f
+#define C6 0.38268343236508977f
+#define C7 0.19509032201612825f
+
+// Orthonormal 8-point DCT-II in place: X_k = a_k sum_n x_n cos((2n+1) k pi / 16), a_0 = 1/sqrt(8), a_k = 1/2.
+__device__ __forceinline__ void dct8_1d(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
+                                        float& x7) {
+    const float s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
+    const float d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
+    const float e0 = s0 + s3, e1 = s1 + s2, e2 = s1 - s2, e3 = s0 - s3;
+    x0 = (e0 + e1) * (0.5f * C4);
+    x4 = (e0 - e1) * (0.5f * C4);
+    x2 = fmaf(e3, 0.5f * C2, e2 * (0.5f * C6));
+    x6 = fmaf(e3, 0.5f * C6, e2 * (-0.5f * C2));
+    x1 = fmaf(d3, 0.5f * C7, fmaf(d2, 0.5f * C5, fmaf(d1, 0.5f * C3, d0 * (0.5f * C1))));
+    x3 = fmaf(d3, -0.5f * C5, fmaf(d2, -0.5f * C1, fmaf(d1, -0.5f * C7, d0 * (0.5f * C3))));
+    x5 = fmaf(d3, 0.5f * C3, fmaf(d2, 0.5f * C7, fmaf(d1, -0.5f * C1, d0 * (0.5f * C5))));
+    x7 = fmaf(d3, -0.5f * C1, fmaf(d2, 0.5f * C3, fmaf(d1, -0.5f * C5, d0 * (0.5f * C7))));
+}
+
+// Inverse of dct8_1d (orthonormal DCT-III): x_n = sum_k a_k X_k cos((2n+1) k pi / 16).
+// Even coefficients give a part symmetric in n <-> 7-n, odd coefficients an antisymmetric part.
+__device__ __forceinline__ void idct8_1d(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
+                                         float& x7) {
+    const float a = (x0 + x4) * (0.5f * C4), b = (x0 - x4) * (0.5f * C4);
+    const float c = fmaf(x2, 0.5f * C2, x6 * (0.5f * C6)), d = fmaf(x2, 0.5f * C6, x6 * (-0.5f * C2));
+    const float e0 = a + c, e1 = b + d, e2 = b - d, e3 = a - c;
+    const float o0 = fmaf(x7, 0.5f * C7, fmaf(x5, 0.5f * C5, fmaf(x3, 0.5f * C3, x1 * (0.5f * C1))));
+    const float o1 = fmaf(x7, -0.5f * C5, fmaf(x5, -0.5f * C1, fmaf(x3, -0.5f * C7, x1 * (0.5f * C3))));
+    const float o2 = fmaf(x7, 0.5f * C3, fmaf(x5, 0.5f * C7, fmaf(x3, -0.5f * C1, x1 * (0.5f * C5))));
+    const float o3 = fmaf(x7, -0.5f * C1, fmaf(x5, 0.5f * C3, fmaf(x3, -0.5f * C5, x1 * (0.5f * C7))));
+    x0 = e0 + o0; x7 = e0 - o0;
+    x1 = e1 + o1; x6 = e1 - o1;
+    x2 = e2 + o2; x5 = e2 - o2;
+    x3 = e3 + o3; x4 = e3 - o3;
+}
+
+// 2-D transforms of an 8x8 block held in registers (row-major b[8*y+x]).
+__device__ __forceinline__ void dct8x8(float (&b)[64]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y)
+        dct8_1d(b[8 * y], b[8 * y + 1], b[8 * y + 2], b[8 * y + 3], b[8 * y + 4], b[8 * y + 5], b[8 * y + 6], b[8 * y + 7]);
+#pragma unroll
+    for (int x = 0; x < 8; ++x) dct8_1d(b[x], b[8 + x], b[16 + x], b[24 + x], b[32 + x], b[40 + x], b[48 + x], b[56 + x]);
+}
+__device__ __forceinline__ void idct8x8(float (&b)[64]) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) idct8_1d(b[x], b[8 + x], b[16 + x], b[24 + x], b[32 + x], b[40 + x], b[48 + x], b[56 + x]);
+#pragma unroll
+    for (int y = 0; y < 8; ++y)
+        idct8_1d(b[8 * y], b[8 * y + 1], b[8 * y + 2], b[8 * y + 3], b[8 * y + 4], b[8 * y + 5], b[8 * y + 6], b[8 * y + 7]);
+}
+
+}  // namespace b200wm

@@ -1,0 +1,242 @@
+// Colour bracket fused into the DWT/SVD embed and extract.
+//
+// The reference's video drivers wrap every frame plugin call in
+//   uint8 HxWx3 -> float32 -> cv2.cvtColor(BGR2YUV) -> encode/decode -> cv2.cvtColor(YUV2BGR) -> clip -> around -> uint8
+// (src/offmark/video/embedder.py:33-39, src/offmark/video/extractor.py:30-34).  Run as separate
+// kernels that is 3 + 12 + (strided) 24 + 12 + 3 bytes of traffic per pixel; fused it is 3 bytes in
+// and 3 bytes out: the thread that owns an 8x8 tile converts its 64 pixels on the fly, builds the
+// 2x2 sums of the marked channel(s), runs the same SVD quantiser as dwtsvd.cu, adds the increments
+// in YUV space and converts back.  Same OpenCV float formulas (fused multiply-adds) as bracket.cu.
+#include "common.cuh"
+#include "svd4.cuh"
+#include "dwtsvd_tile.cuh"
+
+namespace b200wm {
+
+struct RgbArgs {
+    const uint8_t* src;
+    uint8_t* dst;
+    long long frame_stride;
+    unsigned pitch;            // bytes per row (3*width when tight)
+    float scale[3];            // per YUV channel; <= 0: channel untouched (reference: scales=[0,15,0])
+};
+
+__device__ __forceinline__ void px_to_yuv(float c0, float c1, float c2, float& y, float& u, float& v) {
+    y = fmaf(c0, 0.114f, fmaf(c1, 0.587f, c2 * 0.299f));
+    u = fmaf(c0 - y, 0.492f, 0.5f);
+    v = fmaf(c2 - y, 0.877f, 0.5f);
+}
+
+__device__ __forceinline__ unsigned sat_u8(float f) {
+    return (unsigned)__float2int_rn(fminf(fmaxf(f, 0.0f), 255.0f));
+}
+
+// bytes of one tile row: 8 pixels x 3 channels = 24 bytes = 6 words
+template <bool kAligned>
+__device__ __forceinline__ void load_row24(const uint8_t* p, unsigned (&w)[6]) {
+    if (kAligned) {
+        const uint2* q = reinterpret_cast<const uint2*>(p);
+        const uint2 a = q[0], b = q[1], c = q[2];
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            w[k] = (unsigned)p[4 * k] | ((unsigned)p[4 * k + 1] << 8) | ((unsigned)p[4 * k + 2] << 16) | ((unsigned)p[4 * k + 3] << 24);
+    }
+}
+
+__device__ __forceinline__ float byte_of(const unsigned (&w)[6], int i) {
+    return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+}
+
+template <bool kAligned>
+__global__ void __launch_bounds__(128) dwtsvd_embed_rgb8_kernel(RgbArgs a, EmbedArgs em, TileGeom g, int frame0) {
+    const int frame = frame0 + blockIdx.y;
+    const unsigned c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= (unsigned)g.n_tiles) return;
+    const unsigned ty = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
+    const unsigned tx = c - ty * g.tiles_x;
+    const int row = em.frame_row ? em.frame_row[frame] : 0;
+    const int bit = (em.wm[(long long)row * em.wm_words + (c >> 5)] >> (c & 31)) & 1;
+    const long long off = frame * a.frame_stride + (unsigned long long)(ty * 8) * a.pitch + tx * 24;
+
+    unsigned raw[8][6];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) load_row24<kAligned>(a.src + off + (unsigned long long)r * a.pitch, raw[r]);
+
+    // increments of the three YUV channels per 2x2 (zero where the channel is not marked)
+    float D[3][16];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        if (!(a.scale[ch] > 0.0f)) {            // warp-uniform
+#pragma unroll
+            for (int k = 0; k < 16; ++k) D[ch][k] = 0.0f;
+            continue;
+        }
+        float S[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float q[4];
+#pragma unroll
+                for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const int px = 2 * j + dx;
+                        float y, u, v;
+                        px_to_yuv(byte_of(raw[2 * i + dy], 3 * px), byte_of(raw[2 * i + dy], 3 * px + 1),
+                                  byte_of(raw[2 * i + dy], 3 * px + 2), y, u, v);
+                        q[2 * dy + dx] = ch == 0 ? y : (ch == 1 ? u : v);
+                    }
+                S[4 * i + j] = (q[0] + q[1]) + (q[2] + q[3]);
+            }
+        embed_deltas<false>(S, bit, a.scale[ch], 1.0f / a.scale[ch], 0.0f, D[ch], nullptr);
+    }
+
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        unsigned out[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int px = 0; px < 8; ++px) {
+            float y, u, v;
+            px_to_yuv(byte_of(raw[r], 3 * px), byte_of(raw[r], 3 * px + 1), byte_of(raw[r], 3 * px + 2), y, u, v);
+            const int k = 4 * (r >> 1) + (px >> 1);
+            y += D[0][k]; u += D[1][k]; v += D[2][k];
+            const float du = u - 0.5f, dv = v - 0.5f;
+            const float c0 = fmaf(du, 2.032f, y);
+            const float c1 = fmaf(dv, -0.581f, fmaf(du, -0.395f, y));
+            const float c2 = fmaf(dv, 1.14f, y);
+            const int b0 = 3 * px;
+            out[b0 >> 2] |= sat_u8(c0) << (8 * (b0 & 3));
+            out[(b0 + 1) >> 2] |= sat_u8(c1) << (8 * ((b0 + 1) & 3));
+            out[(b0 + 2) >> 2] |= sat_u8(c2) << (8 * ((b0 + 2) & 3));
+        }
+        uint8_t* o = a.dst + off + (unsigned long long)r * a.pitch;
+        if (kAligned) {
+            uint2* q = reinterpret_cast<uint2*>(o);
+            q[0] = make_uint2(out[0], out[1]); q[1] = make_uint2(out[2], out[3]); q[2] = make_uint2(out[4], out[5]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 24; ++k) o[k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
+template <bool kAligned>
+__global__ void __launch_bounds__(128) dwtsvd_extract_rgb8_kernel(RgbArgs a, int channel, ExtractArgs ex, TileGeom g, int frame0) {
+    const int frame = frame0 + blockIdx.y;
+    const unsigned c = blockIdx.x * 128 + threadIdx.x;
+    const unsigned word = c >> 5;
+    const bool live = word < (unsigned)g.words;
+    int bit = 0;
+    if (c < (unsigned)g.n_tiles) {
+        const unsigned ty = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
+        const unsigned tx = c - ty * g.tiles_x;
+        const long long off = frame * a.frame_stride + (unsigned long long)(ty * 8) * a.pitch + tx * 24;
+        float S[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned r0[6], r1[6];
+            load_row24<kAligned>(a.src + off + (unsigned long long)(2 * i) * a.pitch, r0);
+            load_row24<kAligned>(a.src + off + (unsigned long long)(2 * i + 1) * a.pitch, r1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float q[4];
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int px = 2 * j + dx;
+                    float y, u, v;
+                    px_to_yuv(byte_of(r0, 3 * px), byte_of(r0, 3 * px + 1), byte_of(r0, 3 * px + 2), y, u, v);
+                    q[dx] = channel == 0 ? y : (channel == 1 ? u : v);
+                    px_to_yuv(byte_of(r1, 3 * px), byte_of(r1, 3 * px + 1), byte_of(r1, 3 * px + 2), y, u, v);
+                    q[2 + dx] = channel == 0 ? y : (channel == 1 ? u : v);
+                }
+                S[4 * i + j] = (q[0] + q[1]) + (q[2] + q[3]);
+            }
+        }
+        float sigma;
+        bit = extract_bit(S, ex.scale, ex.inv_scale, sigma);
+    }
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
+    const unsigned lane = threadIdx.x & 31;
+    if (lane == 0 && live) ex.raw_bits[(long long)frame * g.words + word] = ballot;
+    if (ex.pos_counts) {
+        __shared__ int cta_counts[32];
+        const int L = ex.payload_len;
+        if (threadIdx.x < 32) cta_counts[threadIdx.x] = 0;
+        __syncthreads();
+        if ((int)lane < L) {
+            const int n = __popc(ballot & (ex.every << lane));
+            if (n) atomicAdd(&cta_counts[lane], n);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < L && cta_counts[threadIdx.x])
+            atomicAdd(&ex.pos_counts[(long long)frame * L + threadIdx.x], cta_counts[threadIdx.x]);
+    }
+}
+
+int launch_vote_counts(const uint32_t* raw_bits, int n_frames, int words_per_frame, long long block_num,
+                       int payload_len, int32_t* pos_counts, cudaStream_t stream);
+
+static int check_rgb(const void* src, int n_frames, int height, int width, long long pitch, long long frame_stride) {
+    if (!src || n_frames < 0 || height <= 0 || width <= 0) return B200WM_ERR_INVALID;
+    if (pitch < 3ll * width || pitch >= (1ll << 31)) return B200WM_ERR_INVALID;
+    if (n_frames > 1 && frame_stride < pitch * height) return B200WM_ERR_INVALID;
+    if ((long long)height * width / 64 >= (1ll << 26)) return B200WM_ERR_UNSUPPORTED;
+    return B200WM_OK;
+}
+
+int launch_embed_rgb8(const uint8_t* src, uint8_t* dst, int n_frames, int height, int width, long long pitch,
+                      long long frame_stride, const float* scales, const uint32_t* wm, int wm_words, long long wm_len,
+                      const int32_t* frame_row, cudaStream_t stream) {
+    int rc = check_rgb(src, n_frames, height, width, pitch, frame_stride);
+    if (rc) return rc;
+    if (!dst || !scales || !wm || wm_words <= 0) return B200WM_ERR_INVALID;
+    const TileGeom g = make_geom(height, width);
+    if (wm_len < g.n_tiles || (long long)wm_words * 32 < g.n_tiles) return B200WM_ERR_SHORT_WM;
+    if (g.n_tiles == 0 || n_frames == 0) return B200WM_OK;
+    RgbArgs a{src, dst, frame_stride, (unsigned)pitch, {scales[0], scales[1], scales[2]}};
+    EmbedArgs ea{wm, frame_row, wm_words, 0.0f, 0.0f};
+    const bool aligned = ((uintptr_t)src % 8) == 0 && ((uintptr_t)dst % 8) == 0 && pitch % 8 == 0 && frame_stride % 8 == 0;
+    const unsigned gx = (g.n_tiles + 127) / 128;
+    for (int f0 = 0; f0 < n_frames; f0 += 65535) {
+        const dim3 grid(gx, (unsigned)((n_frames - f0) < 65535 ? (n_frames - f0) : 65535));
+        if (aligned) dwtsvd_embed_rgb8_kernel<true><<<grid, 128, 0, stream>>>(a, ea, g, f0);
+        else dwtsvd_embed_rgb8_kernel<false><<<grid, 128, 0, stream>>>(a, ea, g, f0);
+        B200WM_LAUNCH_CHECK("dwtsvd_embed_rgb8_kernel");
+    }
+    return B200WM_OK;
+}
+
+int launch_extract_rgb8(const uint8_t* src, int n_frames, int height, int width, long long pitch, long long frame_stride,
+                        int channel, float scale, uint32_t* raw_bits, int words_per_frame, int payload_len,
+                        int32_t* pos_counts, cudaStream_t stream) {
+    int rc = check_rgb(src, n_frames, height, width, pitch, frame_stride);
+    if (rc) return rc;
+    if (!raw_bits || channel < 0 || channel > 2 || !(scale > 0.0f)) return B200WM_ERR_INVALID;
+    if (pos_counts && payload_len <= 0) return B200WM_ERR_INVALID;
+    const TileGeom g = make_geom(height, width);
+    if (words_per_frame != g.words) return B200WM_ERR_INVALID;
+    if (n_frames == 0) return B200WM_OK;
+    const bool fused = pos_counts && payload_len <= 32 && (32 % payload_len) == 0;
+    if (fused) B200WM_CUDA_TRY(cudaMemsetAsync(pos_counts, 0, sizeof(int32_t) * (size_t)n_frames * payload_len, stream));
+    if (g.words > 0) {
+        RgbArgs a{src, nullptr, frame_stride, (unsigned)pitch, {0.0f, 0.0f, 0.0f}};
+        ExtractArgs xa{raw_bits, fused ? pos_counts : nullptr, nullptr, payload_len, fused ? every_mask(payload_len) : 0u, scale,
+                       1.0f / scale};
+        const bool aligned = ((uintptr_t)src % 8) == 0 && pitch % 8 == 0 && frame_stride % 8 == 0;
+        const unsigned gx = ((unsigned)g.words * 32 + 127) / 128;
+        for (int f0 = 0; f0 < n_frames; f0 += 65535) {
+            const dim3 grid(gx, (unsigned)((n_frames - f0) < 65535 ? (n_frames - f0) : 65535));
+            if (aligned) dwtsvd_extract_rgb8_kernel<true><<<grid, 128, 0, stream>>>(a, channel, xa, g, f0);
+            else dwtsvd_extract_rgb8_kernel<false><<<grid, 128, 0, stream>>>(a, channel, xa, g, f0);
+            B200WM_LAUNCH_CHECK("dwtsvd_extract_rgb8_kernel");
+        }
+    }
+    if (pos_counts && !fused)
+        return launch_vote_counts(raw_bits, n_frames, words_per_frame, g.block_num, payload_len, pos_counts, stream);
+    return B200WM_OK;
+}
+
+}  // namespace b200wm

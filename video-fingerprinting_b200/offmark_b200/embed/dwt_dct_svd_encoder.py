@@ -39,6 +39,12 @@ class DwtDctSvdEncoder:
             ops.dwtsvd_embed_(frame.dev, packed, n, scale=self.scales[channel], channel=channel)
         return frame.write_back()
 
+    def mark_rgb8(self, frames):
+        """uint8 ``[N, H, W, 3]`` / ``[H, W, 3]`` CUDA frames marked in place in ONE kernel: the colour
+        bracket of ``Embedder.__mark_frame`` (video/embedder.py:33-39) fused around ``encode``."""
+        packed, n = self._packed_wm(frames.device)
+        return ops.dwtsvd_embed_rgb8_(frames, packed, n, scales=self.scales)
+
     def encode_planes(self, planes, scale=None, frame_wm_row=None, wm_rows=None, out=None):
         """Batched form for device-resident planes (``[N, H, W]`` uint8 or float32): one launch
         for the whole batch.  ``wm_rows`` (2-D 0/1 array) with ``frame_wm_row`` (int32 ``[N]``)

@@ -31,6 +31,17 @@ class DwtDctSvdDecoder:
         bits = ops.unpack_bits(raw, self.block_num).astype(np.float64).reshape(1, -1)
         return RawBits(bits, packed=raw, block_num=self.block_num)
 
+    def decode_rgb8(self, frame):
+        """uint8 ``[H, W, 3]`` CUDA frame -> the same ``(1, N)`` float64 array as ``decode`` of its YUV
+        conversion (video/extractor.py:31-32), colour conversion fused into the extract kernel."""
+        rows, cols, _ = frame.shape
+        self.block_num = rows * cols // 4 // (self.blk * self.blk)
+        if self.scales[1] <= 0:
+            return np.zeros((1, self.block_num))
+        raw, _ = ops.dwtsvd_extract_rgb8(frame, scale=self.scales[1], channel=1)
+        bits = ops.unpack_bits(raw, self.block_num).astype(np.float64).reshape(1, -1)
+        return RawBits(bits, packed=raw, block_num=self.block_num)
+
     def decode_planes(self, planes, scale=None, payload_len=None):
         """Batched form for device-resident planes: -> (raw_bits int32 [N, words],
         pos_counts int32 [N, payload_len] or None), everything left on the GPU."""

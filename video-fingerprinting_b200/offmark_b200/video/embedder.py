@@ -37,6 +37,8 @@ class Embedder:
         """uint8 H x W x 3 in, uint8 H x W x 3 out (numpy)."""
         dev = device_of(self.device)
         frame = torch.from_numpy(np.ascontiguousarray(frame_rgb, dtype=np.uint8)).to(dev)
+        if hasattr(self.frame_embedder, "mark_rgb8"):        # colour bracket fused into the plugin's kernel
+            return self.frame_embedder.mark_rgb8(frame).cpu().numpy()
         yuv = ops.bgr8_to_yuv32(frame)
         yuv = self.frame_embedder.encode(yuv)
         return ops.yuv32_to_bgr8(yuv).cpu().numpy()

@@ -34,5 +34,8 @@ class Extractor:
     def check_frame(self, frame_rgb):
         dev = device_of(self.device)
         frame = torch.from_numpy(np.ascontiguousarray(frame_rgb, dtype=np.uint8)).to(dev)
-        bits = self.frame_extractor.decode(ops.bgr8_to_yuv32(frame))
+        if hasattr(self.frame_extractor, "decode_rgb8"):     # colour conversion fused into the extract kernel
+            bits = self.frame_extractor.decode_rgb8(frame)
+        else:
+            bits = self.frame_extractor.decode(ops.bgr8_to_yuv32(frame))
         return self.degenerator.degenerate(bits)
