@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the headline bench line): 4K planes, the fused rgb24 path, the 8x8
+DCT pair and the attack kernels, each timed with CUDA events on HBM-resident data larger than L2.
+Prints one JSON object per case."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "video-fingerprinting_b200"))
+
+import numpy as np      # noqa: E402
+import torch            # noqa: E402
+
+from b200wm import ops  # noqa: E402
+from offmark_b200.generator.shuffler import Shuffler  # noqa: E402
+
+DEV = torch.device("cuda:0")
+PEAK = 6552.6
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", PEAK)
+
+
+def timed(fn, warmup=3, steps=10):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def report(name, ms, frames, bytes_per_frame, **extra):
+    gbs = frames * bytes_per_frame / (ms * 1e-3) / 1e9
+    print(json.dumps({"case": name, "ms": round(ms, 4), "frames": frames, "frames_per_s": round(frames / (ms * 1e-3)),
+                      "algorithmic_GBs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / PEAK, 3), **extra}), flush=True)
+
+
+def planes(n, h, w, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    base = 128 + 60 * torch.sin(torch.arange(w, device=DEV) / 41.0)[None, None, :] * torch.cos(torch.arange(h, device=DEV) / 29.0)[None, :, None]
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=DEV)
+    for f0 in range(0, n, 32):
+        m = min(32, n - f0)
+        out[f0:f0 + m] = (base + 6 * torch.randn((m, h, w), device=DEV, generator=g)).round().clamp(16, 235).to(torch.uint8)
+    return out
+
+
+def main():
+    payload = np.array([0, 1, 1, 0, 0, 1, 0, 1])
+    # ---- 4K Y planes (BASELINE config 3, one GPU's shard)
+    h, w, n = 2160, 3840, 256
+    src = planes(n, h, w)
+    dst = src.clone()
+    wm, ln = ops.pack_bits(Shuffler(key=0).generate_wm(payload, (1, h * w // 64))[0], device=DEV)
+    for path, tag in ((0, "tma"), (1, "ldg")):
+        ops.set_path(path)
+        ms_e = timed(lambda: ops.dwtsvd_embed_(src, wm, ln, out=dst))
+        ms_x = timed(lambda: ops.dwtsvd_extract(dst, payload_len=8))
+        report(f"4K embed ({tag})", ms_e, n, 2 * h * w)
+        report(f"4K extract ({tag})", ms_x, n, h * w)
+        report(f"4K embed+extract ({tag})", ms_e + ms_x, n, 3 * h * w)
+    ops.set_path(0)
+    del src, dst
+    # ---- fused rgb24 1080p frames (reference default flow: U channel of the converted frame)
+    h, w, n = 1080, 1920, 512
+    # coloured content: three different smooth fields plus noise, so chroma is not a flat 0.5
+    frames = torch.stack([planes(n, h, w, seed=s).roll(37 * s, dims=2).roll(11 * s, dims=1) for s in range(3)], dim=3)
+    frames[..., 0] = (frames[..., 0].float() * 0.6 + 90).clamp(0, 255).to(torch.uint8)
+    frames = frames.contiguous()
+    wm, ln = ops.pack_bits(Shuffler(key=0).generate_wm(payload, (1, h * w // 64))[0], device=DEV)
+    ms_e = timed(lambda: ops.dwtsvd_embed_rgb8_(frames, wm, ln))
+    ms_x = timed(lambda: ops.dwtsvd_extract_rgb8(frames, payload_len=8))
+    report("rgb24 fused embed (in place, 6 B/px)", ms_e, n, 6 * h * w)
+    report("rgb24 fused extract (3 B/px)", ms_x, n, 3 * h * w)
+
+    def unfused():
+        yuv = ops.bgr8_to_yuv32(frames[:128])
+        ops.dwtsvd_embed_(yuv, wm, ln, channel=1)
+        return ops.yuv32_to_bgr8(yuv)
+    report("rgb24 three-kernel embed (bracket + strided float32 embed + bracket)", timed(unfused), 128, 6 * h * w)
+    del frames
+    # ---- 8x8 DCT pair on float32 interleaved YUV (the reference layout)
+    n = 128
+    yuv = torch.rand((n, h, w, 3), device=DEV) * 200 + 20
+    ms_m = timed(lambda: ops.dct8_masks(yuv, channel=0))
+    masks = ops.dct8_masks(yuv, channel=0)
+    ms_e = timed(lambda: ops.dct8_embed_(yuv, masks, wm, ln, alpha=20, channel=1))
+    ms_x = timed(lambda: ops.dct8_extract(yuv, masks, alpha=20, payload_len=8, channel=1))
+    report("dct8 masks (float32 interleaved, Y read)", ms_m, n, 4 * h * w)
+    report("dct8 embed (U read+write)", ms_e, n, 8 * h * w)
+    report("dct8 extract (U read)", ms_x, n, 4 * h * w)
+    del yuv
+    # ---- attack kernels
+    y = planes(512, h, w)
+    report("jpeg-like requant q75 (in place)", timed(lambda: ops.attack_jpeg_requant_(y, 75)), 512, 2 * h * w)
+
+
+if __name__ == "__main__":
+    main()

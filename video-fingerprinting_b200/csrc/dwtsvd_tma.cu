@@ -286,7 +286,9 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const u
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-constexpr size_t kMaxRingBytes = 200 * 1024;
+// three 15 KB strips (1080p) leave room for four CTAs per SM; wider planes would starve the SM of
+// warps (two CTAs at 4K), where the vectorised-load kernels measured faster (profiles/r01_summary.md)
+constexpr size_t kMaxRingBytes = 56 * 1024;
 
 bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const TileGeom& g) {
     return pl->dtype == B200WM_U8 && pl->elem_stride == 1 && pl->pitch_bytes == pl->width && (pl->width % 16) == 0 &&

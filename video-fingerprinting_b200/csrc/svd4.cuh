@@ -21,7 +21,7 @@
 namespace b200wm {
 
 constexpr float kTau = 5.8207661e-11f;     // 2^-34 relative bound on lambda_0 - lambda
-constexpr int kPowerIters = 8;
+constexpr int kSquarings = 8;               // slow path: G^(2^j) steps before giving up on power iteration
 
 // Symmetric 4x4 in packed upper-triangular order: 00 01 02 03 11 12 13 22 23 33.
 __device__ __forceinline__ void gram4(const float (&S)[16], float (&G)[10]) {
@@ -125,6 +125,27 @@ static __device__ __noinline__ Top5 top_pair_jacobi(float s0, float s1, float s2
     return Top5{out[0], out[1], out[2], out[3], out[4]};
 }
 
+// H <- H*H for a symmetric 4x4 in packed upper-triangular order, renormalised by an exact power
+// of two so that its trace stays in [0.5, 1).
+__device__ __forceinline__ void square_sym4(float (&H)[10]) {
+    const float a = H[0], b = H[1], c = H[2], d = H[3], e = H[4], f = H[5], g = H[6], h = H[7], i = H[8], j = H[9];
+    float R[10];
+    R[0] = fmaf(d, d, fmaf(c, c, fmaf(b, b, a * a)));
+    R[1] = fmaf(d, g, fmaf(c, f, fmaf(b, e, a * b)));
+    R[2] = fmaf(d, i, fmaf(c, h, fmaf(b, f, a * c)));
+    R[3] = fmaf(d, j, fmaf(c, i, fmaf(b, g, a * d)));
+    R[4] = fmaf(g, g, fmaf(f, f, fmaf(e, e, b * b)));
+    R[5] = fmaf(g, i, fmaf(f, h, fmaf(e, f, b * c)));
+    R[6] = fmaf(g, j, fmaf(f, i, fmaf(e, g, b * d)));
+    R[7] = fmaf(i, i, fmaf(h, h, fmaf(f, f, c * c)));
+    R[8] = fmaf(i, j, fmaf(h, i, fmaf(f, g, c * d)));
+    R[9] = fmaf(j, j, fmaf(i, i, fmaf(g, g, d * d)));
+    const float tr = (R[0] + R[4]) + (R[7] + R[9]);
+    const float down = __uint_as_float(0x7E800000u - (__float_as_uint(tr) & 0x7F800000u));
+#pragma unroll
+    for (int k = 0; k < 10; ++k) H[k] = R[k] * down;
+}
+
 // One power step with the convergence test.  x is the current iterate, w = G x.
 // Returns true when the Kato-Temple bound certifies lambda (see the header comment).
 __device__ __forceinline__ bool rayleigh_check(const float (&x)[4], const float (&w)[4], float tr, float& xw, float& xx) {
@@ -167,10 +188,21 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
     float xw, xx;
     bool done = rayleigh_check(x, w, tr, xw, xx) || zero_block;
     if (!done) {
-#pragma unroll 1
-        for (int it = 0; it < kPowerIters && !done; ++it) {
+        // Slow convergence (second singular value close to the first, typical of chroma planes
+        // whose mean is near zero): power steps with G^2, G^4, G^8, ... - the convergence ratio is
+        // squared every round - while the certificate is always evaluated with G itself.
+        float H[10];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = w[k];
+        for (int k = 0; k < 10; ++k) H[k] = G[k];
+#pragma unroll 1
+        for (int round = 0; round < kSquarings && !done; ++round) {
+            square_sym4(H);
+            symv4(H, w, x);
+            // keep the iterate's magnitude in range: exact power-of-two rescale by its largest entry
+            const float m = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
+            const float up2 = __uint_as_float(0x7E800000u - (__float_as_uint(m) & 0x7F800000u));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] *= up2;
             symv4(G, x, w);
             done = rayleigh_check(x, w, tr, xw, xx);
         }
