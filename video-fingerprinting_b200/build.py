@@ -50,7 +50,8 @@ def build_library(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB_PATH] + srcs
+    extra = os.environ.get("B200WM_NVCC_EXTRA", "").split()      # tuning experiments only (e.g. -DB200WM_EXTRACT_STAGES=2)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB_PATH] + srcs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)

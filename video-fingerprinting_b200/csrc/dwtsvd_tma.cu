@@ -25,8 +25,8 @@
 //     and the embed kernel funnel-shifts its 32 watermark bits out of two words.
 //
 // Requirements (otherwise the launcher uses the vectorised-load kernels): planar uint8 with
-// tight rows (pitch == width), width a multiple of 16, base and frame stride multiples of 16
-// bytes, at least 64 tiles per row, and three strips fitting in shared memory.
+// tight rows (pitch == width), width a multiple of 16 between 512 and 2048 (one tile per thread,
+// three strips per CTA and four CTAs per SM), base and frame stride multiples of 16 bytes.
 #include "common.cuh"
 #include "svd4.cuh"
 #include "dwtsvd_tile.cuh"
@@ -34,7 +34,17 @@
 namespace b200wm {
 
 constexpr int kStripThreads = 256;
-constexpr int kStages = 3;
+#ifndef B200WM_EMBED_STAGES
+#define B200WM_EMBED_STAGES 3
+#endif
+constexpr int kEmbedStages = B200WM_EMBED_STAGES;      // >= 3: load in flight + strip being updated + store in flight
+#ifndef B200WM_EXTRACT_STAGES
+#define B200WM_EXTRACT_STAGES 3
+#endif
+#ifndef B200WM_EXTRACT_MIN_CTAS
+#define B200WM_EXTRACT_MIN_CTAS 4
+#endif
+constexpr int kExtractStages = B200WM_EXTRACT_STAGES;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -104,6 +114,7 @@ __device__ __forceinline__ long long strip_offset(const Item& it, const StripGeo
     return it.frame * sg.frame_stride + (long long)it.ty * sg.strip_bytes;
 }
 
+template <int kStages>
 __device__ __forceinline__ void init_ring(unsigned bar0) {
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -115,8 +126,9 @@ __device__ __forceinline__ void init_ring(unsigned bar0) {
 
 // ---- extract -------------------------------------------------------------------------------------------
 // raw_bits must be zero on entry (the launcher clears it): warps OR their bits in.
-__global__ void __launch_bounds__(kStripThreads) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src, ExtractArgs ex,
+__global__ void __launch_bounds__(kStripThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src, ExtractArgs ex,
                                                                           StripGeom sg) {
+    constexpr int kStages = kExtractStages;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long bars[kStages];
     __shared__ int cta_counts[2][32];        // per-strip vote counts, double-buffered by iteration parity
@@ -125,7 +137,7 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_extract_tma_kernel(const
     const int lane = threadIdx.x & 31;
     const TileGeom& g = sg.g;
     if (threadIdx.x < 64) cta_counts[threadIdx.x >> 5][threadIdx.x & 31] = 0;
-    init_ring(bar0);
+    init_ring<kStages>(bar0);
 
     Item it{(int)blockIdx.x / g.tiles_y, (int)blockIdx.x % g.tiles_y};
     if (threadIdx.x == 0) {          // prologue: fill the ring
@@ -146,60 +158,69 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_extract_tma_kernel(const
     int stage = 0, flip = 0;
     unsigned parity = 0;
     const int L = ex.payload_len;
+    const int t = threadIdx.x;                       // one pass: the launcher guarantees tiles_x <= kStripThreads
+    const bool live = t < g.tiles_x;
+    const bool warp_live = (t & ~31) < g.tiles_x;    // warp-uniform
+    int prev_frame = -1;
     for (; it.frame < sg.n_frames; advance(it, sg), advance(ahead, sg), flip ^= 1) {
         const unsigned slot = ring + stage * sg.strip_bytes;
         mbar_wait(bar0 + 8 * stage, parity);
-        for (int t0 = 0; t0 < g.tiles_x; t0 += kStripThreads) {      // one pass at 1080p, two at 4K
-            const int t = t0 + threadIdx.x;
-            const bool live = t < g.tiles_x;
-            int bit = 0;
-            if (live) {
-                float S[16];
-                {
-                    uint2 rows[8];
+        float S[16];
+        if (live) {
+            uint2 rows[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) rows[r] = lds_u2(slot + r * sg.pitch + t * 8);
-                    sums_from_rows(rows, S);
-                }
-                float sigma;
-                bit = extract_bit(S, ex.scale, ex.inv_scale, sigma);
-            }
-            if (t0 + (threadIdx.x & ~31) < g.tiles_x) {                 // warp-uniform: this warp holds tiles
-                const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
-                const unsigned c0 = (unsigned)(it.ty * g.tiles_x + t0 + (threadIdx.x & ~31));
-                const unsigned sh = c0 & 31u;
-                if (lane == 0 && ballot) {
-                    uint32_t* w = ex.raw_bits + (long long)it.frame * g.words + (c0 >> 5);
-                    atomicOr(w, ballot << sh);
-                    if (sh && (ballot >> (32u - sh))) atomicOr(w + 1, ballot >> (32u - sh));
-                }
-                if (ex.pos_counts && lane < L) {
-                    // lane i sees the bits of blocks c0+i, c0+i+L, ...: payload position (c0 + i) mod L
-                    const int n = __popc(ballot & (ex.every << lane));
-                    if (n) atomicAdd(&cta_counts[flip][(c0 + lane) & (unsigned)(L - 1)], n);
-                }
-            }
+            for (int r = 0; r < 8; ++r) rows[r] = lds_u2(slot + r * sg.pitch + t * 8);
+            sums_from_rows(rows, S);
         }
-        __syncthreads();             // every thread has consumed its bytes: the slot may be overwritten
-        if (ex.pos_counts && (int)threadIdx.x < L) {
-            // one global update per position and strip; this buffer is next touched two barriers from now
-            const int n = cta_counts[flip][threadIdx.x];
-            if (n) {
-                atomicAdd(&ex.pos_counts[(long long)it.frame * L + threadIdx.x], n);
-                cta_counts[flip][threadIdx.x] = 0;
-            }
-        }
-        if (threadIdx.x == 0 && ahead.frame < sg.n_frames) {
+        // Early barrier: the warps arrive together (they all just waited on the same mbarrier) and the
+        // slot is handed back to the copy engine before the eigen-iteration, not after it.
+        __syncthreads();
+        if (t == 0 && ahead.frame < sg.n_frames) {
             mbar_arrive_expect_tx(bar0 + 8 * stage, sg.strip_bytes);
             bulk_load(slot, src + strip_offset(ahead, sg), sg.strip_bytes, bar0 + 8 * stage);
         }
+        if (ex.pos_counts && t < L && prev_frame >= 0) {
+            // votes of the previous strip: complete since the barrier above; its buffer is reused two barriers from now
+            const int n = cta_counts[flip ^ 1][t];
+            if (n) {
+                atomicAdd(&ex.pos_counts[(long long)prev_frame * L + t], n);
+                cta_counts[flip ^ 1][t] = 0;
+            }
+        }
+        prev_frame = it.frame;
+        int bit = 0;
+        if (live) {
+            float sigma;
+            bit = extract_bit(S, ex.scale, ex.inv_scale, sigma);
+        }
+        if (warp_live) {
+            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
+            const unsigned c0 = (unsigned)(it.ty * g.tiles_x + (t & ~31));
+            const unsigned sh = c0 & 31u;
+            if (lane == 0 && ballot) {
+                uint32_t* w = ex.raw_bits + (long long)it.frame * g.words + (c0 >> 5);
+                atomicOr(w, ballot << sh);
+                if (sh && (ballot >> (32u - sh))) atomicOr(w + 1, ballot >> (32u - sh));
+            }
+            if (ex.pos_counts && lane < L) {
+                // lane i sees the bits of blocks c0+i, c0+i+L, ...: payload position (c0 + i) mod L
+                const int n = __popc(ballot & (ex.every << lane));
+                if (n) atomicAdd(&cta_counts[flip][(c0 + lane) & (unsigned)(L - 1)], n);
+            }
+        }
         if (++stage == kStages) { stage = 0; parity ^= 1u; }
+    }
+    __syncthreads();
+    if (ex.pos_counts && t < L && prev_frame >= 0) {
+        const int n = cta_counts[flip ^ 1][t];
+        if (n) atomicAdd(&ex.pos_counts[(long long)prev_frame * L + t], n);
     }
 }
 
 // ---- embed ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                         EmbedArgs em, StripGeom sg) {
+    constexpr int kStages = kEmbedStages;
     static_assert(kStages >= 3, "a slot is refilled one iteration after its store was committed");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long bars[kStages];
@@ -207,7 +228,7 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const u
     const unsigned bar0 = smem_u32(&bars[0]);
     const int lane = threadIdx.x & 31;
     const TileGeom& g = sg.g;
-    init_ring(bar0);
+    init_ring<kStages>(bar0);
 
     Item it{(int)blockIdx.x / g.tiles_y, (int)blockIdx.x % g.tiles_y};
     if (threadIdx.x == 0) {
@@ -233,37 +254,33 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const u
         // row; issued before the wait so that their latency hides behind it
         const int row = em.frame_row ? em.frame_row[it.frame] : 0;
         const uint32_t* wrow = em.wm + (long long)row * em.wm_words;
-        auto warp_bits = [&](int t0) -> unsigned {
-            const unsigned c0 = (unsigned)(it.ty * g.tiles_x + t0 + (threadIdx.x & ~31));
-            const int wi = (int)(c0 >> 5);
-            if (wi >= em.wm_words) return 0u;
+        const int t = threadIdx.x;                   // one pass: the launcher guarantees tiles_x <= kStripThreads
+        const unsigned c0 = (unsigned)(it.ty * g.tiles_x + (t & ~31));
+        const int wi = (int)(c0 >> 5);
+        unsigned bits = 0u;
+        if (wi < em.wm_words) {
             const unsigned lo = wrow[wi], hi = (wi + 1 < em.wm_words) ? wrow[wi + 1] : 0u;
-            return __funnelshift_r(lo, hi, c0 & 31u);
-        };
-        unsigned bits = warp_bits(0);
+            bits = __funnelshift_r(lo, hi, c0 & 31u);
+        }
         mbar_wait(bar0 + 8 * stage, parity);
-        for (int t0 = 0; t0 < g.tiles_x; t0 += kStripThreads) {
-            const int t = t0 + threadIdx.x;
-            if (t0 > 0) bits = warp_bits(t0);
-            if (t < g.tiles_x) {
-                const unsigned mine = slot + t * 8;
-                float S[16], D[16];
-                {
-                    uint2 rows[8];
+        if (t < g.tiles_x) {
+            const unsigned mine = slot + t * 8;
+            float S[16], D[16];
+            {
+                uint2 rows[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) rows[r] = lds_u2(mine + r * sg.pitch);
-                    sums_from_rows(rows, S);
-                }
-                embed_deltas<false>(S, (bits >> lane) & 1u, em.scale, em.inv_scale, 12582912.0f, D, nullptr);
+                for (int r = 0; r < 8; ++r) rows[r] = lds_u2(mine + r * sg.pitch);
+                sums_from_rows(rows, S);
+            }
+            embed_deltas<false>(S, (bits >> lane) & 1u, em.scale, em.inv_scale, 12582912.0f, D, nullptr);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const unsigned d01 = __byte_perm(__float_as_uint(D[4 * i + 0]), __float_as_uint(D[4 * i + 1]), 0x5410);
-                    const unsigned d23 = __byte_perm(__float_as_uint(D[4 * i + 2]), __float_as_uint(D[4 * i + 3]), 0x5410);
+            for (int i = 0; i < 4; ++i) {
+                const unsigned d01 = __byte_perm(__float_as_uint(D[4 * i + 0]), __float_as_uint(D[4 * i + 1]), 0x5410);
+                const unsigned d23 = __byte_perm(__float_as_uint(D[4 * i + 2]), __float_as_uint(D[4 * i + 3]), 0x5410);
 #pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const unsigned a = mine + (2 * i + rr) * sg.pitch;
-                        sts_u2(a, add_clamp_row(lds_u2(a), d01, d23));
-                    }
+                for (int rr = 0; rr < 2; ++rr) {
+                    const unsigned a = mine + (2 * i + rr) * sg.pitch;
+                    sts_u2(a, add_clamp_row(lds_u2(a), d01, d23));
                 }
             }
         }
@@ -293,8 +310,8 @@ constexpr size_t kMaxRingBytes = 56 * 1024;
 bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const TileGeom& g) {
     return pl->dtype == B200WM_U8 && pl->elem_stride == 1 && pl->pitch_bytes == pl->width && (pl->width % 16) == 0 &&
            ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && (pl->frame_stride_bytes % 16) == 0 &&
-           (pl->n_frames <= 1 || pl->frame_stride_bytes >= pl->pitch_bytes * (long long)pl->height) && g.tiles_x >= 64 &&
-           g.tiles_y > 0 && (size_t)kStages * 8 * (size_t)pl->pitch_bytes <= kMaxRingBytes &&
+           (pl->n_frames <= 1 || pl->frame_stride_bytes >= pl->pitch_bytes * (long long)pl->height) && g.tiles_x >= 64 && g.tiles_x <= kStripThreads &&
+           g.tiles_y > 0 && (size_t)kEmbedStages * 8 * (size_t)pl->pitch_bytes <= kMaxRingBytes &&
            (long long)pl->n_frames * g.tiles_y < (1ll << 31);
 }
 
@@ -327,7 +344,7 @@ static StripGeom make_strip_geom(const TileGeom& g, const b200wm_plane* pl, int 
 }
 
 int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const TileGeom& g, ExtractArgs xa, cudaStream_t stream) {
-    const size_t smem = (size_t)kStages * 8 * (size_t)pl->pitch_bytes;
+    const size_t smem = (size_t)kExtractStages * 8 * (size_t)pl->pitch_bytes;
     int blocks = 0;
     int rc = persistent_grid(dwtsvd_extract_tma_kernel, smem, &blocks);
     if (rc) return rc;
@@ -340,7 +357,7 @@ int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const Til
 
 int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, const TileGeom& g, EmbedArgs ea,
                             cudaStream_t stream) {
-    const size_t smem = (size_t)kStages * 8 * (size_t)pl->pitch_bytes;
+    const size_t smem = (size_t)kEmbedStages * 8 * (size_t)pl->pitch_bytes;
     int blocks = 0;
     int rc = persistent_grid(dwtsvd_embed_tma_kernel, smem, &blocks);
     if (rc) return rc;
