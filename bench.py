@@ -386,6 +386,16 @@ def main():
     achieved = embed_gbs if k_embed >= k_extract else extract_gbs
     step_gbs = 3.0 * W * H * n_frames / (ms_per_step * 1e-3) / 1e9
 
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this very
+    # launch size (profiles/r01_traffic.json); null when the workload differs from the captured one
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and n_frames == 3000:
+        with open(tpath) as f:
+            cap = json.load(f)["kernels"].get(dominant)
+        if cap and cap.get("frames") == n_frames:
+            traffic = cap["traffic_bytes"]
+
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -393,7 +403,7 @@ def main():
         "gpu_launches": launches, "clocks": clocks,
         "kernel_path": "tma_persistent" if args.path == 0 else "ldg_vectorised",
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": (2 if dominant.startswith("dwtsvd_embed") else 1) * W * H * n_frames},
         "kernels": {"embed_ms": k_embed, "embed_GBs": embed_gbs, "extract_ms": k_extract, "extract_GBs": extract_gbs,
                     "vote_and_combine_ms": k_vote, "step_GBs": step_gbs, "step_frac_of_peak": step_gbs / peak,
