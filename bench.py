@@ -424,60 +424,44 @@ def main():
 
 
 def run_e2e(args, ops, deg, src, wm_packed, wm_len, frame_row, block_num, words, dev, payloads, world=1):
-    """Same metric through host buffers: pinned host Y planes -> GPU -> embed -> marked planes back to
-    the host; marked host planes -> GPU -> extract + per-frame vote -> patterns back to the host.
-    Chunked and double-buffered over two streams so copies overlap the kernels."""
+    """Same metric through the C ABI's HOST-buffer entry points: pinned host Y planes ->
+    b200wm_dwtsvd_mark_host (H2D, embed, D2H of the marked planes) -> b200wm_dwtsvd_detect_host on the
+    marked host planes (H2D, extract, per-frame vote, D2H of the patterns).  Copies, kernels and
+    downloads of successive 125-frame chunks overlap on two streams inside the library."""
     import torch.distributed as dist
     n = min(args.e2e_frames, src.shape[0])
     host_in = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
     host_marked = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
-    host_patterns = torch.empty((n, PAYLOAD_LEN), dtype=torch.uint8, pin_memory=True)
     host_in.copy_(src[:n])
     torch.cuda.synchronize()
+    rows_host = ops.unpack_bits(wm_packed, wm_len)                   # [segments, block_num] 0/1 on the host
+    frame_row_host = frame_row[:n].cpu()
+    perm = deg.payload_idx
     chunk = 125
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    bufs = [torch.empty((chunk, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
-    raws = [torch.empty((chunk, words), dtype=torch.int32, device=dev) for _ in range(2)]
-    cnts = [torch.empty((chunk, PAYLOAD_LEN), dtype=torch.int32, device=dev) for _ in range(2)]
+    patterns = None
 
     def one_pass():
-        for phase in ("mark", "detect"):
-            for i, f0 in enumerate(range(0, n, chunk)):
-                m = min(chunk, n - f0)
-                s, b = streams[i % 2], bufs[i % 2][:m]
-                with torch.cuda.stream(s):
-                    if phase == "mark":
-                        b.copy_(host_in[f0:f0 + m], non_blocking=True)
-                        ops.dwtsvd_embed_(b, wm_packed, wm_len, scale=15.0, frame_wm_row=frame_row[f0:f0 + m].contiguous())
-                        host_marked[f0:f0 + m].copy_(b, non_blocking=True)
-                    else:
-                        b.copy_(host_marked[f0:f0 + m], non_blocking=True)
-                        r, c = raws[i % 2][:m], cnts[i % 2][:m]
-                        ops.dwtsvd_extract(b, scale=15.0, payload_len=PAYLOAD_LEN, raw_bits=r, pos_counts=c)
-                        patterns, _ = deg.degenerate_counts(c, block_num)
-                        host_patterns[f0:f0 + m].copy_(patterns, non_blocking=True)
-            for s in streams:
-                s.synchronize()
+        ops.dwtsvd_mark_host(host_in, host_marked, rows_host, scale=15.0, frame_wm_row=frame_row_host, chunk_frames=chunk)
+        return ops.dwtsvd_detect_host(host_marked, perm, scale=15.0, chunk_frames=chunk)
 
     one_pass()
-    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     steps = max(2, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
-        one_pass()
-    torch.cuda.synchronize()
+        patterns = one_pass()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    ok = float((host_patterns.numpy() == payloads[np.arange(n) // SEGMENT_FRAMES]).all(axis=1).mean())
+    ok = float((patterns == payloads[np.arange(n) // SEGMENT_FRAMES]).all(axis=1).mean())
     return {"value": n * world * steps / dt, "unit": "frames/s", "h2d_bytes_per_step": 2 * n * H * W,
             "d2h_bytes_per_step": n * H * W + n * PAYLOAD_LEN, "frames_per_gpu": n, "steps": steps,
-            "path": "pinned host Y planes -> H2D -> embed -> D2H marked; marked -> H2D -> extract+vote -> D2H patterns; "
-                    "125-frame chunks on 2 streams", "frames_exact": ok}
+            "path": "b200wm_dwtsvd_mark_host + b200wm_dwtsvd_detect_host on pinned host Y planes (H2D, embed, D2H marked; "
+                    "H2D marked, extract + vote, D2H patterns), 125-frame chunks on 2 streams inside the library",
+            "frames_exact": ok}
 
 
 if __name__ == "__main__":

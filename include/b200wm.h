@@ -228,6 +228,26 @@ B200WM_API int b200wm_dwtsvd_extract_rgb8(const uint8_t* src, int32_t n_frames, 
                               int64_t frame_stride_bytes, int32_t channel, float scale, uint32_t* raw_bits,
                               int32_t words_per_frame, int32_t payload_len, int32_t* pos_counts, void* stream);
 
+/* ---- host-buffer entry points ---------------------------------------------------------------------- */
+/*
+ * The whole path on frames that live in HOST memory, as the reference's drivers see them (frames
+ * come from and go to ffmpeg pipes, video/frame_reader.py:53-64, video/frame_writer.py:41-44).
+ * `plane` describes planar uint8 planes in host memory; every other pointer is a host pointer too.
+ * The batch is streamed through the current device in chunks of `chunk_frames` (0 = automatic) on
+ * two internal streams (upload, kernels and download overlap); the calls return when the results
+ * are in host memory.  Pinned host memory gives full PCIe speed.
+ *
+ * mark:   Embedder's per-frame encode for the whole batch (b200wm_dwtsvd_embed semantics).
+ * detect: DwtDctSvdDecoder.decode + DeShuffler.degenerate per frame: patterns_host [n_frames, payload_len]
+ *         uint8; raw_bits_host [n_frames, words] and pos_counts_host [n_frames, payload_len] are optional.
+ */
+B200WM_API int b200wm_dwtsvd_mark_host(const uint8_t* src_host, uint8_t* dst_host, const b200wm_plane* plane,
+                           const uint32_t* wm_packed_host, int32_t n_wm_rows, int32_t wm_words, int64_t wm_len,
+                           const int32_t* frame_wm_row_host, float scale, int32_t chunk_frames);
+B200WM_API int b200wm_dwtsvd_detect_host(const uint8_t* src_host, const b200wm_plane* plane, float scale, int32_t payload_len,
+                             const int32_t* perm_host, uint8_t* patterns_host, uint32_t* raw_bits_host,
+                             int32_t* pos_counts_host, int32_t chunk_frames);
+
 /* ---- distortion channel for robustness studies (no counterpart in the reference) ---- */
 /*
  * JPEG-like requantisation of planar uint8 planes: per 8x8 block DCT(x-128), quantise and dequantise

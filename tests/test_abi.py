@@ -19,7 +19,7 @@ def _header_functions():
 def test_header_symbols_are_exported_and_bound():
     from b200wm import _lib
     names = _header_functions()
-    assert len(names) >= 25
+    assert len(names) >= 27
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for n in names:
         assert hasattr(raw, n), f"{n} declared in b200wm.h but not exported"

@@ -127,3 +127,36 @@ def test_hls_pattern_collector_flow():
     for f in (0, F + 1, 4 * F + 3):
         bits = o_svd.extract_plane(host[f])
         assert np.array_equal(o_pay.degenerate(bits, 8, KEY), patterns[f].cpu().numpy())
+
+
+def test_host_buffer_entry_points_match_device_path():
+    """b200wm_dwtsvd_mark_host / _detect_host (frames in host memory, chunked double-buffered streaming
+    inside the library) give exactly what the device-resident calls give."""
+    from b200wm import ops
+    from oracle import synth
+    n, h, w = 7, 240, 320
+    planes = np.stack([synth.luma_plane_u8(h, w, f, 9) for f in range(n)])
+    payloads = [o_pay.payload_for_segment(s) for s in (9, 100)]
+    rows = np.stack([o_pay.generate_wm(p, (1, h * w // 64), KEY)[0] for p in payloads])
+    frame_row = np.array([0, 0, 0, 1, 1, 1, 1], dtype=np.int32)
+    # I420-like host layout: planes are strided views of a bigger pinned buffer
+    frame_bytes = h * w * 3 // 2
+    host = torch.zeros((n, frame_bytes), dtype=torch.uint8).pin_memory()
+    src = host.as_strided((n, h, w), (frame_bytes, w, 1))
+    src.copy_(torch.from_numpy(planes))
+    dst = torch.empty_like(host).as_strided((n, h, w), (frame_bytes, w, 1))
+    for chunk in (0, 1, 3):
+        ops.dwtsvd_mark_host(src, dst, rows, frame_wm_row=frame_row, chunk_frames=chunk)
+        dev = torch.from_numpy(planes).cuda()
+        packed, nb = ops.pack_bits(rows, device="cuda")
+        ops.dwtsvd_embed_(dev, packed, nb, frame_wm_row=torch.from_numpy(frame_row).cuda())
+        assert np.array_equal(dst.numpy(), dev.cpu().numpy())
+        patterns, raw = ops.dwtsvd_detect_host(dst, o_pay.permutation(8, KEY), chunk_frames=chunk, want_raw_bits=True)
+        raw_dev, counts = ops.dwtsvd_extract(dev, payload_len=8)
+        assert np.array_equal(raw, raw_dev.cpu().numpy().view(np.uint32))
+        for f in range(n):
+            assert np.array_equal(patterns[f], payloads[frame_row[f]])
+    # in place on the host buffer, pageable memory
+    pageable = planes.copy()
+    ops.dwtsvd_mark_host(pageable, pageable, rows, frame_wm_row=frame_row)
+    assert np.array_equal(pageable, dst.numpy())

@@ -253,3 +253,36 @@ def test_full_size_properties(h, w, n_frames):
     assert (again.int() - marked.int()).abs().float().mean().item() < 0.6
     # checksum of counts equals the popcount of the raw bits
     assert counts.sum(dim=1).cpu().tolist() == [int(b.sum()) for b in bits]
+
+
+def test_no_out_of_bounds_writes_guard_bytes():
+    """compute-sanitizer is closed on this pool, so bounds are checked with canaries: the planes sit
+    inside a larger buffer whose guard bytes (before, after, and the chroma planes between the luma
+    planes of an I420 layout) must come back untouched from embed and extract, on both kernel paths."""
+    from b200wm import ops
+    n, h, w = 5, 72, 1040                       # 130 tiles per row: TMA-eligible, 9 tile rows
+    frame_bytes = h * w * 3 // 2
+    guard = 4096
+    buf = torch.full((guard + n * frame_bytes + guard,), 0xA5, dtype=torch.uint8, device=_dev())
+    frames = buf[guard:guard + n * frame_bytes].view(n, frame_bytes)
+    gen = torch.Generator(device=_dev()).manual_seed(1)
+    y = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device=_dev(), generator=gen)
+    planes = frames.as_strided((n, h, w), (frame_bytes, w, 1))
+    planes.copy_(y)
+    wm = _wm((h, w))
+    packed, nb = ops.pack_bits(wm[0], device=_dev())
+    ops.dwtsvd_embed_(planes, packed, nb)
+    raw, counts = ops.dwtsvd_extract(planes, payload_len=8)
+    torch.cuda.synchronize()
+    host = buf.cpu().numpy()
+    assert (host[:guard] == 0xA5).all() and (host[-guard:] == 0xA5).all()
+    chroma = host[guard:guard + n * frame_bytes].reshape(n, frame_bytes)[:, h * w:]
+    assert (chroma == 0xA5).all(), "embed wrote outside the luma planes"
+    marked = planes.cpu().numpy()
+    for f in range(n):
+        want = o_svd.embed_plane_u8(y[f].cpu().numpy(), wm[0])
+        _, edge_floor, _ = knife_edge_blocks(y[f].cpu().numpy().astype(np.float32))
+        ok = ~tile_mask_to_pixels(edge_floor, (h, w))
+        assert np.abs(marked[f].astype(np.int16) - want)[ok].max() <= 1
+    # the output buffers are exactly sized too
+    assert raw.shape == (n, (h * w // 64 + 31) // 32) and counts.shape == (n, 8)

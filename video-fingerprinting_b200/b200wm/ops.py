@@ -291,6 +291,56 @@ def dwtsvd_extract_rgb8(frames, scale=15.0, channel=1, payload_len=None):
     return raw_bits, pos_counts
 
 
+# ----------------------------------------------------------------------------- host-buffer entry points
+def _host_planes(t):
+    """CPU uint8 tensor [N, H, W] (any positive strides with contiguous rows) -> (tensor, plane)."""
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(t)
+    if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.uint8 or t.dim() != 3 or t.stride(2) != 1:
+        raise ValueError("host planes must be a CPU uint8 [N, H, W] array with contiguous rows")
+    n, h, w = t.shape
+    return t, Plane(_lib.U8, n, h, w, t.stride(1), t.stride(0) if n > 1 else 0, 1, 0)
+
+
+def dwtsvd_mark_host(src, dst, wm_rows, scale=15.0, frame_wm_row=None, chunk_frames=0):
+    """Mark host-resident planes: ``src``/``dst`` CPU uint8 ``[N, H, W]`` (pinned for full PCIe speed; may be
+    the same array), ``wm_rows`` 0/1 array ``[rows, n]``.  One C-ABI call; copies and kernels overlap inside."""
+    require_cuda()
+    s, pl = _host_planes(src)
+    d, dpl = _host_planes(dst)
+    if (dpl.height, dpl.width, dpl.n_frames, dpl.pitch_bytes, dpl.frame_stride_bytes) != \
+            (pl.height, pl.width, pl.n_frames, pl.pitch_bytes, pl.frame_stride_bytes):
+        raise ValueError("dst must have the geometry of src")
+    packed, n = pack_bits(wm_rows)
+    rows = None
+    if frame_wm_row is not None:
+        rows = torch.as_tensor(frame_wm_row, dtype=torch.int32).contiguous()
+        if rows.numel() != pl.n_frames:
+            raise ValueError("frame_wm_row needs one entry per frame")
+    check(lib.b200wm_dwtsvd_mark_host(C.c_void_p(s.data_ptr()), C.c_void_p(d.data_ptr()), C.byref(pl), C.c_void_p(packed.data_ptr()),
+                                      packed.shape[0], packed.shape[1], int(n),
+                                      C.c_void_p(rows.data_ptr()) if rows is not None else None, float(scale), int(chunk_frames)))
+    return dst
+
+
+def dwtsvd_detect_host(src, perm, scale=15.0, chunk_frames=0, want_raw_bits=False):
+    """Extract + per-frame vote of host-resident planes -> patterns uint8 ``[N, L]`` (numpy)
+    [, raw bits uint32 ``[N, words]``]."""
+    require_cuda()
+    s, pl = _host_planes(src)
+    perm = torch.as_tensor(np.asarray(perm), dtype=torch.int32).contiguous()
+    length = perm.numel()
+    _, _, words = geometry(pl.height, pl.width)
+    patterns = torch.empty((pl.n_frames, length), dtype=torch.uint8)
+    raw = torch.empty((pl.n_frames, max(words, 1)), dtype=torch.int32) if want_raw_bits else None
+    check(lib.b200wm_dwtsvd_detect_host(C.c_void_p(s.data_ptr()), C.byref(pl), float(scale), length, C.c_void_p(perm.data_ptr()),
+                                        C.c_void_p(patterns.data_ptr()), C.c_void_p(raw.data_ptr()) if raw is not None else None,
+                                        None, int(chunk_frames)))
+    if want_raw_bits:
+        return patterns.numpy(), raw[:, :words].numpy().view(np.uint32)
+    return patterns.numpy()
+
+
 # ----------------------------------------------------------------------------- distortion channel
 def attack_jpeg_requant_(planes, quality):
     """In-place JPEG-like requantisation of planar uint8 planes (BASELINE config 5)."""

@@ -32,6 +32,8 @@ int launch_attack_noise(const void*, void*, const b200wm_plane*, const float*, c
 int launch_embed_rgb8(const uint8_t*, uint8_t*, int, int, int, long long, long long, const float*, const uint32_t*, int, long long,
                       const int32_t*, cudaStream_t);
 int launch_extract_rgb8(const uint8_t*, int, int, int, long long, long long, int, float, uint32_t*, int, int, int32_t*, cudaStream_t);
+int mark_host(const uint8_t*, uint8_t*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float, int);
+int detect_host(const uint8_t*, const b200wm_plane*, float, int, const int32_t*, uint8_t*, uint32_t*, int32_t*, int);
 void set_path(int);
 int get_path();
 int launch_yuv32_to_bgr8(const float*, uint8_t*, long long, cudaStream_t);
@@ -174,6 +176,18 @@ B200WM_API int b200wm_dwtsvd_extract_rgb8(const uint8_t* src, int32_t n_frames, 
                               int32_t words_per_frame, int32_t payload_len, int32_t* pos_counts, void* stream) {
     return launch_extract_rgb8(src, n_frames, height, width, pitch_bytes, frame_stride_bytes, channel, scale, raw_bits,
                                words_per_frame, payload_len, pos_counts, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_dwtsvd_mark_host(const uint8_t* src_host, uint8_t* dst_host, const b200wm_plane* plane,
+                           const uint32_t* wm_packed_host, int32_t n_wm_rows, int32_t wm_words, int64_t wm_len,
+                           const int32_t* frame_wm_row_host, float scale, int32_t chunk_frames) {
+    return mark_host(src_host, dst_host, plane, wm_packed_host, n_wm_rows, wm_words, wm_len, frame_wm_row_host, scale, chunk_frames);
+}
+
+B200WM_API int b200wm_dwtsvd_detect_host(const uint8_t* src_host, const b200wm_plane* plane, float scale, int32_t payload_len,
+                             const int32_t* perm_host, uint8_t* patterns_host, uint32_t* raw_bits_host,
+                             int32_t* pos_counts_host, int32_t chunk_frames) {
+    return detect_host(src_host, plane, scale, payload_len, perm_host, patterns_host, raw_bits_host, pos_counts_host, chunk_frames);
 }
 
 }  // extern "C"
