@@ -39,9 +39,23 @@ struct Scratch {
 int copy_planes(void* dst, const void* src, const b200wm_plane* pl, int frames, bool to_device, cudaStream_t s) {
     const size_t row = (size_t)pl->width, plane = row * pl->height;
     const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-    if (pl->pitch_bytes == pl->width) {          // every plane is one contiguous run: one 2-D copy per chunk
-        if (to_device) B200WM_CUDA_TRY(cudaMemcpy2DAsync(dst, plane, src, (size_t)pl->frame_stride_bytes, plane, frames, kind, s));
-        else B200WM_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)pl->frame_stride_bytes, src, plane, plane, frames, kind, s));
+    if (pl->pitch_bytes == pl->width && (frames == 1 || pl->frame_stride_bytes == (long long)plane)) {
+        // the whole chunk is one contiguous run on both sides
+        if (to_device) B200WM_CUDA_TRY(cudaMemcpyAsync(dst, src, plane * frames, kind, s));
+        else B200WM_CUDA_TRY(cudaMemcpyAsync(dst, src, plane * frames, kind, s));
+        return B200WM_OK;
+    }
+    if (pl->pitch_bytes == pl->width) {
+        // every plane is one contiguous run (e.g. the Y plane of an I420 frame): one plain copy per
+        // frame - measured much faster than a single 2-D copy whose "rows" are whole planes
+        for (int f = 0; f < frames; ++f) {
+            if (to_device)
+                B200WM_CUDA_TRY(cudaMemcpyAsync((uint8_t*)dst + f * plane, (const uint8_t*)src + (size_t)f * pl->frame_stride_bytes,
+                                                plane, kind, s));
+            else
+                B200WM_CUDA_TRY(cudaMemcpyAsync((uint8_t*)dst + (size_t)f * pl->frame_stride_bytes, (const uint8_t*)src + f * plane,
+                                                plane, kind, s));
+        }
         return B200WM_OK;
     }
     for (int f = 0; f < frames; ++f) {
