@@ -8,8 +8,9 @@ patterns of a segment are joined to strings, ``Counter(...).most_common(1)`` pic
 Frames and segments shard across GPUs (one process per GPU).  Each rank accumulates, with
 ``b200wm_pattern_hist``, a histogram of patterns per segment, the earliest global frame index
 of each pattern, the per-bit vote counters and the frame counts; ``combine`` merges the ranks
-with two all-reduces (SUM of the counters, MIN of the first-seen indices) - a few KB over
-NCCL/NVLink - after which every rank can reproduce ``most_common(1)`` exactly.
+with one all-gather of the flat state (a few tens of KB over NCCL/NVLink; SUM of the counters and
+MIN of the first-seen indices are then taken locally), after which every rank can reproduce
+``most_common(1)`` exactly.
 """
 from collections import Counter
 
@@ -30,13 +31,16 @@ class SegmentVote:
         self.n_segments, self.payload_len = int(n_segments), int(payload_len)
         dev = torch.device(device)
         bins = 1 << self.payload_len
-        # one flat int32 buffer so that the SUM part is a single all-reduce
-        self._sum = torch.zeros(self.n_segments * (bins + self.payload_len + 1), dtype=torch.int32, device=dev)
-        self.first_seen = torch.full((self.n_segments, bins), ops.INT32_MAX, dtype=torch.int32, device=dev)
+        # one flat int32 buffer [hist | bit_votes | seg_frames | first_seen] so that ONE collective moves it all
         a, b = self.n_segments * bins, self.n_segments * (bins + self.payload_len)
-        self.hist = self._sum[:a].view(self.n_segments, bins)
-        self.bit_votes = self._sum[a:b].view(self.n_segments, self.payload_len)
-        self.seg_frames = self._sum[b:].view(self.n_segments)
+        c = b + self.n_segments
+        self._flat = torch.zeros(c + self.n_segments * bins, dtype=torch.int32, device=dev)
+        self._n_sum = c
+        self.hist = self._flat[:a].view(self.n_segments, bins)
+        self.bit_votes = self._flat[a:b].view(self.n_segments, self.payload_len)
+        self.seg_frames = self._flat[b:c].view(self.n_segments)
+        self.first_seen = self._flat[c:].view(self.n_segments, bins)
+        self.first_seen.fill_(ops.INT32_MAX)
 
     def _state(self):
         return {"hist": self.hist, "first_seen": self.first_seen, "bit_votes": self.bit_votes,
@@ -49,10 +53,16 @@ class SegmentVote:
         return self
 
     def combine(self, group=None):
-        """Merge the ranks' counters.  No-op without an initialised process group."""
+        """Merge the ranks' counters: one all-gather of the flat state (tens of KB per rank, latency-bound
+        over NVLink), then SUM of the counters and MIN of the first-seen indices locally.  No-op
+        without an initialised process group."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self._sum, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(self.first_seen, op=dist.ReduceOp.MIN, group=group)
+            world = dist.get_world_size(group)
+            parts = [torch.empty_like(self._flat) for _ in range(world)]
+            dist.all_gather(parts, self._flat, group=group)
+            stacked = torch.stack(parts)
+            self._flat[:self._n_sum] = stacked[:, :self._n_sum].sum(dim=0, dtype=torch.int32)
+            self._flat[self._n_sum:] = stacked[:, self._n_sum:].amin(dim=0)
         return self
 
     def result(self):

@@ -49,8 +49,10 @@ __device__ __forceinline__ float byte_of(const unsigned (&w)[6], int i) {
     return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
 }
 
-template <bool kAligned>
-__global__ void __launch_bounds__(128) dwtsvd_embed_rgb8_kernel(RgbArgs a, EmbedArgs em, TileGeom g, int frame0) {
+// kMask: bit c set = YUV channel c is marked (scale[c] > 0); compile-time so that unmarked channels
+// cost neither registers nor instructions (the reference default, scales=[0,15,0], is kMask = 2).
+template <bool kAligned, int kMask>
+__global__ void __launch_bounds__(128, 4) dwtsvd_embed_rgb8_kernel(RgbArgs a, EmbedArgs em, TileGeom g, int frame0) {
     const int frame = frame0 + blockIdx.y;
     const unsigned c = blockIdx.x * 128 + threadIdx.x;
     if (c >= (unsigned)g.n_tiles) return;
@@ -60,49 +62,47 @@ __global__ void __launch_bounds__(128) dwtsvd_embed_rgb8_kernel(RgbArgs a, Embed
     const int bit = (em.wm[(long long)row * em.wm_words + (c >> 5)] >> (c & 31)) & 1;
     const long long off = frame * a.frame_stride + (unsigned long long)(ty * 8) * a.pitch + tx * 24;
 
-    unsigned raw[8][6];
+    // Pass A: 2x2 sums of the marked channels.  The 192 source bytes are NOT kept in registers across
+    // the eigen-iteration; pass B re-reads them row by row (L1 hits).
+    float S[3][16];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) load_row24<kAligned>(a.src + off + (unsigned long long)r * a.pitch, raw[r]);
-
-    // increments of the three YUV channels per 2x2 (zero where the channel is not marked)
+    for (int i = 0; i < 4; ++i) {
+        unsigned r0[6], r1[6];
+        load_row24<kAligned>(a.src + off + (unsigned long long)(2 * i) * a.pitch, r0);
+        load_row24<kAligned>(a.src + off + (unsigned long long)(2 * i + 1) * a.pitch, r1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float y[4], u[4], v[4];
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int px = 2 * j + dx;
+                px_to_yuv(byte_of(r0, 3 * px), byte_of(r0, 3 * px + 1), byte_of(r0, 3 * px + 2), y[dx], u[dx], v[dx]);
+                px_to_yuv(byte_of(r1, 3 * px), byte_of(r1, 3 * px + 1), byte_of(r1, 3 * px + 2), y[2 + dx], u[2 + dx], v[2 + dx]);
+            }
+            if (kMask & 1) S[0][4 * i + j] = (y[0] + y[1]) + (y[2] + y[3]);
+            if (kMask & 2) S[1][4 * i + j] = (u[0] + u[1]) + (u[2] + u[3]);
+            if (kMask & 4) S[2][4 * i + j] = (v[0] + v[1]) + (v[2] + v[3]);
+        }
+    }
     float D[3][16];
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        if (!(a.scale[ch] > 0.0f)) {            // warp-uniform
-#pragma unroll
-            for (int k = 0; k < 16; ++k) D[ch][k] = 0.0f;
-            continue;
-        }
-        float S[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float q[4];
-#pragma unroll
-                for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 2; ++dx) {
-                        const int px = 2 * j + dx;
-                        float y, u, v;
-                        px_to_yuv(byte_of(raw[2 * i + dy], 3 * px), byte_of(raw[2 * i + dy], 3 * px + 1),
-                                  byte_of(raw[2 * i + dy], 3 * px + 2), y, u, v);
-                        q[2 * dy + dx] = ch == 0 ? y : (ch == 1 ? u : v);
-                    }
-                S[4 * i + j] = (q[0] + q[1]) + (q[2] + q[3]);
-            }
-        embed_deltas<false>(S, bit, a.scale[ch], 1.0f / a.scale[ch], 0.0f, D[ch], nullptr);
-    }
+    for (int ch = 0; ch < 3; ++ch)
+        if (kMask & (1 << ch)) embed_deltas<false>(S[ch], bit, a.scale[ch], 1.0f / a.scale[ch], 0.0f, D[ch], nullptr);
 
+    // Pass B: convert again, add the increments in YUV space, convert back, clip, round, store.
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
+        unsigned raw[6];
+        load_row24<kAligned>(a.src + off + (unsigned long long)r * a.pitch, raw);
         unsigned out[6] = {0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
         for (int px = 0; px < 8; ++px) {
             float y, u, v;
-            px_to_yuv(byte_of(raw[r], 3 * px), byte_of(raw[r], 3 * px + 1), byte_of(raw[r], 3 * px + 2), y, u, v);
+            px_to_yuv(byte_of(raw, 3 * px), byte_of(raw, 3 * px + 1), byte_of(raw, 3 * px + 2), y, u, v);
             const int k = 4 * (r >> 1) + (px >> 1);
-            y += D[0][k]; u += D[1][k]; v += D[2][k];
+            if (kMask & 1) y += D[0][k];
+            if (kMask & 2) u += D[1][k];
+            if (kMask & 4) v += D[2][k];
             const float du = u - 0.5f, dv = v - 0.5f;
             const float c0 = fmaf(du, 2.032f, y);
             const float c1 = fmaf(dv, -0.581f, fmaf(du, -0.395f, y));
@@ -194,6 +194,8 @@ int launch_embed_rgb8(const uint8_t* src, uint8_t* dst, int n_frames, int height
     if (rc) return rc;
     if (!dst || !scales || !wm || wm_words <= 0) return B200WM_ERR_INVALID;
     const TileGeom g = make_geom(height, width);
+    const int mask = (scales[0] > 0.0f ? 1 : 0) | (scales[1] > 0.0f ? 2 : 0) | (scales[2] > 0.0f ? 4 : 0);
+    if (mask == 0) return B200WM_OK;             // nothing to mark: the reference's loop skips every channel
     if (wm_len < g.n_tiles || (long long)wm_words * 32 < g.n_tiles) return B200WM_ERR_SHORT_WM;
     if (g.n_tiles == 0 || n_frames == 0) return B200WM_OK;
     RgbArgs a{src, dst, frame_stride, (unsigned)pitch, {scales[0], scales[1], scales[2]}};
@@ -202,8 +204,16 @@ int launch_embed_rgb8(const uint8_t* src, uint8_t* dst, int n_frames, int height
     const unsigned gx = (g.n_tiles + 127) / 128;
     for (int f0 = 0; f0 < n_frames; f0 += 65535) {
         const dim3 grid(gx, (unsigned)((n_frames - f0) < 65535 ? (n_frames - f0) : 65535));
-        if (aligned) dwtsvd_embed_rgb8_kernel<true><<<grid, 128, 0, stream>>>(a, ea, g, f0);
-        else dwtsvd_embed_rgb8_kernel<false><<<grid, 128, 0, stream>>>(a, ea, g, f0);
+#define B200WM_RGB_CASE(M)                                                                          \
+    case M:                                                                                         \
+        if (aligned) dwtsvd_embed_rgb8_kernel<true, M><<<grid, 128, 0, stream>>>(a, ea, g, f0);      \
+        else dwtsvd_embed_rgb8_kernel<false, M><<<grid, 128, 0, stream>>>(a, ea, g, f0);             \
+        break;
+        switch (mask) {
+            B200WM_RGB_CASE(1) B200WM_RGB_CASE(2) B200WM_RGB_CASE(3) B200WM_RGB_CASE(4)
+            B200WM_RGB_CASE(5) B200WM_RGB_CASE(6) B200WM_RGB_CASE(7)
+        }
+#undef B200WM_RGB_CASE
         B200WM_LAUNCH_CHECK("dwtsvd_embed_rgb8_kernel");
     }
     return B200WM_OK;
