@@ -91,23 +91,25 @@ __device__ __forceinline__ void sts_u2(unsigned addr, uint2 v) {
 }
 
 // ---- work items ---------------------------------------------------------------------------------------
-struct Item {
-    int frame, ty;
-};
-
+// Strips are numbered i = frame * tiles_y + ty; CTA b processes i = b, b + grid, b + 2*grid, ...
 struct StripGeom {
     TileGeom g;
-    int n_frames;
-    int step_frames, step_ty;        // grid size split into whole frames and tile rows
+    int total;                       // n_frames * tiles_y  (< 2^26 so that the magic division is exact)
+    unsigned long long ty_magic;     // i / tiles_y == (i * magic) >> 40
     unsigned pitch;                  // == width
     unsigned strip_bytes;            // 8 * pitch
     long long frame_stride;
 };
 
-__device__ __forceinline__ void advance(Item& it, const StripGeom& sg) {
-    it.frame += sg.step_frames;
-    it.ty += sg.step_ty;
-    if (it.ty >= sg.g.tiles_y) { it.ty -= sg.g.tiles_y; ++it.frame; }
+struct Item {
+    int frame, ty;
+};
+
+__device__ __forceinline__ Item item_of(int i, const StripGeom& sg) {
+    Item it;
+    it.frame = (int)(((unsigned long long)(unsigned)i * sg.ty_magic) >> 40);
+    it.ty = i - it.frame * sg.g.tiles_y;
+    return it;
 }
 
 __device__ __forceinline__ long long strip_offset(const Item& it, const StripGeom& sg) {
@@ -139,21 +141,17 @@ __global__ void __launch_bounds__(kStripThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd
     if (threadIdx.x < 64) cta_counts[threadIdx.x >> 5][threadIdx.x & 31] = 0;
     init_ring<kStages>(bar0);
 
-    Item it{(int)blockIdx.x / g.tiles_y, (int)blockIdx.x % g.tiles_y};
+    const int step = (int)gridDim.x;
     if (threadIdx.x == 0) {          // prologue: fill the ring
-        Item p = it;
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
-            if (p.frame < sg.n_frames) {
+            const int i = (int)blockIdx.x + s * step;
+            if (i < sg.total) {
                 mbar_arrive_expect_tx(bar0 + 8 * s, sg.strip_bytes);
-                bulk_load(ring + s * sg.strip_bytes, src + strip_offset(p, sg), sg.strip_bytes, bar0 + 8 * s);
+                bulk_load(ring + s * sg.strip_bytes, src + strip_offset(item_of(i, sg), sg), sg.strip_bytes, bar0 + 8 * s);
             }
-            advance(p, sg);
         }
     }
-    Item ahead = it;                 // the strip kStages iterations ahead (what a freed slot is refilled with)
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) advance(ahead, sg);
 
     int stage = 0, flip = 0;
     unsigned parity = 0;
@@ -162,7 +160,8 @@ __global__ void __launch_bounds__(kStripThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd
     const bool live = t < g.tiles_x;
     const bool warp_live = (t & ~31) < g.tiles_x;    // warp-uniform
     int prev_frame = -1;
-    for (; it.frame < sg.n_frames; advance(it, sg), advance(ahead, sg), flip ^= 1) {
+    for (int i = (int)blockIdx.x; i < sg.total; i += step, flip ^= 1) {
+        const Item it = item_of(i, sg);
         const unsigned slot = ring + stage * sg.strip_bytes;
         mbar_wait(bar0 + 8 * stage, parity);
         float S[16];
@@ -175,9 +174,9 @@ __global__ void __launch_bounds__(kStripThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd
         // Early barrier: the warps arrive together (they all just waited on the same mbarrier) and the
         // slot is handed back to the copy engine before the eigen-iteration, not after it.
         __syncthreads();
-        if (t == 0 && ahead.frame < sg.n_frames) {
+        if (t == 0 && i + kStages * step < sg.total) {     // refill with the strip kStages iterations ahead
             mbar_arrive_expect_tx(bar0 + 8 * stage, sg.strip_bytes);
-            bulk_load(slot, src + strip_offset(ahead, sg), sg.strip_bytes, bar0 + 8 * stage);
+            bulk_load(slot, src + strip_offset(item_of(i + kStages * step, sg), sg), sg.strip_bytes, bar0 + 8 * stage);
         }
         if (ex.pos_counts && t < L && prev_frame >= 0) {
             // votes of the previous strip: complete since the barrier above; its buffer is reused two barriers from now
@@ -230,25 +229,22 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const u
     const TileGeom& g = sg.g;
     init_ring<kStages>(bar0);
 
-    Item it{(int)blockIdx.x / g.tiles_y, (int)blockIdx.x % g.tiles_y};
+    const int step = (int)gridDim.x;
     if (threadIdx.x == 0) {
-        Item p = it;
 #pragma unroll
         for (int s = 0; s < kStages - 1; ++s) {          // the last slot is filled by the first refill
-            if (p.frame < sg.n_frames) {
+            const int i = (int)blockIdx.x + s * step;
+            if (i < sg.total) {
                 mbar_arrive_expect_tx(bar0 + 8 * s, sg.strip_bytes);
-                bulk_load(ring + s * sg.strip_bytes, src + strip_offset(p, sg), sg.strip_bytes, bar0 + 8 * s);
+                bulk_load(ring + s * sg.strip_bytes, src + strip_offset(item_of(i, sg), sg), sg.strip_bytes, bar0 + 8 * s);
             }
-            advance(p, sg);
         }
     }
-    Item ahead = it;                 // the strip kStages-1 iterations ahead
-#pragma unroll
-    for (int s = 0; s < kStages - 1; ++s) advance(ahead, sg);
 
     int stage = 0, refill = kStages - 1;
     unsigned parity = 0;
-    for (; it.frame < sg.n_frames; advance(it, sg), advance(ahead, sg)) {
+    for (int i = (int)blockIdx.x; i < sg.total; i += step) {
+        const Item it = item_of(i, sg);
         const unsigned slot = ring + stage * sg.strip_bytes;
         // the 32 watermark bits of each warp's tiles, funnel-shifted out of two words of the packed
         // row; issued before the wait so that their latency hides behind it
@@ -291,9 +287,11 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const u
             bulk_commit();
             // the slot stored one iteration ago has been read by now (at most this store pending)
             bulk_wait_read<1>();
-            if (ahead.frame < sg.n_frames) {
+            const int nxt = i + (kStages - 1) * step;     // the strip kStages-1 iterations ahead
+            if (nxt < sg.total) {
                 mbar_arrive_expect_tx(bar0 + 8 * refill, sg.strip_bytes);
-                bulk_load(ring + refill * sg.strip_bytes, src + strip_offset(ahead, sg), sg.strip_bytes, bar0 + 8 * refill);
+                bulk_load(ring + refill * sg.strip_bytes, src + strip_offset(item_of(nxt, sg), sg), sg.strip_bytes,
+                          bar0 + 8 * refill);
             }
         }
         refill = stage;
@@ -312,7 +310,7 @@ bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const Ti
            ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && (pl->frame_stride_bytes % 16) == 0 &&
            (pl->n_frames <= 1 || pl->frame_stride_bytes >= pl->pitch_bytes * (long long)pl->height) && g.tiles_x >= 64 && g.tiles_x <= kStripThreads &&
            g.tiles_y > 0 && (size_t)kEmbedStages * 8 * (size_t)pl->pitch_bytes <= kMaxRingBytes &&
-           (long long)pl->n_frames * g.tiles_y < (1ll << 31);
+           (long long)pl->n_frames * g.tiles_y < (1ll << 26) && (long long)pl->n_frames * g.tiles_y * g.tiles_y < (1ll << 40);
 }
 
 template <typename Kernel>
@@ -331,12 +329,11 @@ static int persistent_grid(Kernel kernel, size_t smem, int* blocks) {
     return B200WM_OK;
 }
 
-static StripGeom make_strip_geom(const TileGeom& g, const b200wm_plane* pl, int blocks) {
+static StripGeom make_strip_geom(const TileGeom& g, const b200wm_plane* pl) {
     StripGeom sg;
     sg.g = g;
-    sg.n_frames = pl->n_frames;
-    sg.step_frames = blocks / g.tiles_y;
-    sg.step_ty = blocks % g.tiles_y;
+    sg.total = pl->n_frames * g.tiles_y;
+    sg.ty_magic = (1ull << 40) / (unsigned long long)g.tiles_y + 1ull;
     sg.pitch = (unsigned)pl->pitch_bytes;
     sg.strip_bytes = 8u * sg.pitch;
     sg.frame_stride = pl->frame_stride_bytes;
@@ -350,7 +347,7 @@ int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const Til
     if (rc) return rc;
     const long long strips = (long long)pl->n_frames * g.tiles_y;
     if (strips < blocks) blocks = (int)strips;
-    dwtsvd_extract_tma_kernel<<<blocks, kStripThreads, smem, stream>>>((const uint8_t*)src, xa, make_strip_geom(g, pl, blocks));
+    dwtsvd_extract_tma_kernel<<<blocks, kStripThreads, smem, stream>>>((const uint8_t*)src, xa, make_strip_geom(g, pl));
     B200WM_LAUNCH_CHECK("dwtsvd_extract_tma_kernel");
     return B200WM_OK;
 }
@@ -364,7 +361,7 @@ int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, 
     const long long strips = (long long)pl->n_frames * g.tiles_y;
     if (strips < blocks) blocks = (int)strips;
     dwtsvd_embed_tma_kernel<<<blocks, kStripThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea,
-                                                                     make_strip_geom(g, pl, blocks));
+                                                                     make_strip_geom(g, pl));
     B200WM_LAUNCH_CHECK("dwtsvd_embed_tma_kernel");
     return B200WM_OK;
 }
