@@ -113,8 +113,10 @@ B200WM_API int32_t b200wm_words_per_frame(int height, int width);
  * blk is fixed at 4.  `dst` may equal `src` (in place, like the reference) or
  * be another buffer of identical geometry that already holds the frames; only
  * the samples of the walked tiles are written.
- * U8 planes are written back as clip(0,255) -> round-half-even -> uint8, the
- * caller bracket of video/embedder.py:37-38; F32 planes are written unrounded.
+ * U8 planes are written back as clip(sample + round-half-even(increment), 0, 255), the caller
+ * bracket of video/embedder.py:37-38 (np.clip, np.around, uint8) up to exact rounding ties: the
+ * reference rounds sample + increment, which differs by 1 LSB only when an increment is exactly
+ * k + 0.5 (observed on 4e-6 of the samples).  F32 planes are written unrounded.
  * wm_packed: [n_wm_rows, wm_words] packed bits; frame f uses row
  * frame_wm_row[f] (NULL -> row 0 for every frame).  wm_len = bits per row.
  */

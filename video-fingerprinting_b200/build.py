@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
-    "-fmad=true",
+    "-fmad=false",     # no implicit contraction: every FMA is written as fmaf, so all kernel families round identically
     "-cudart", "static",
 ]
 

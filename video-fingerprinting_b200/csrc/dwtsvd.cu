@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_kernel(PlaneArgs pl, Em
         for (int y = 0; y < 8; ++y)
 #pragma unroll
             for (int x = 0; x < 8; ++x) {
-                const float f = (float)row_ptr(p, y, pl.pitch)[x * es] + D[4 * (y >> 1) + (x >> 1)];
+                // sample + round-half-even(increment), like the vector path (see add_clamp_row)
+                const float f = (float)row_ptr(p, y, pl.pitch)[x * es] + rintf(D[4 * (y >> 1) + (x >> 1)]);
                 row_ptr(o, y, pl.pitch)[x * es] = (uint8_t)__float2int_rn(fminf(fmaxf(f, 0.0f), 255.0f));
             }
     } else {
