@@ -9,11 +9,14 @@
 //     vector load per thread and row.  (A first version used 2-D tensor-map boxes of 256x8
 //     bytes per warp; ncu showed the copy engine saturating on those small boxes at 2.3 TB/s -
 //     profiles/r01_summary.md - which is why the strips are now whole rows.)
-//   * Each CTA is persistent and owns a ring of kStages strip buffers in shared memory.  One
-//     elected thread issues the bulk loads for the strips the CTA will need next and arms an
-//     mbarrier with the byte count; all threads wait on the barrier's phase.  HBM latency is
-//     hidden by the ring depth, no thread spends issue slots on global address arithmetic and
-//     the 64 source bytes of a tile never occupy registers for the length of the SVD.
+//   * Each CTA is persistent and owns a ring of kStages strip buffers in shared memory.  It is warp
+//     specialised: eight consumer warps do the arithmetic, a ninth PRODUCER warp only moves data.
+//     The producer issues the bulk loads for the strips the CTA will need next and arms a "full"
+//     mbarrier with the byte count; consumers wait on its phase, and each consumer warp arrives
+//     on the slot's "empty" mbarrier when it is done, so consumer warps never wait for each other
+//     (no CTA-wide barrier in the loop).  HBM latency is hidden by the ring depth, no consumer
+//     spends issue slots on global address arithmetic and the 64 source bytes of a tile never
+//     occupy registers for the length of the SVD.
 //   * Thread t owns tile t of the strip: it reads its 8x8 bytes from shared memory
 //     (conflict-free: a warp reads 256 contiguous bytes per row).  Embed updates the strip in
 //     shared memory and writes it back with a bulk store (cp.async.bulk ... bulk_group); a slot
@@ -33,7 +36,9 @@
 
 namespace b200wm {
 
-constexpr int kStripThreads = 256;
+constexpr int kStripThreads = 256;                 // consumer threads: one 8x8 tile each
+constexpr int kConsumerWarps = kStripThreads / 32;
+constexpr int kCtaThreads = kStripThreads + 32;    // + the producer warp
 #ifndef B200WM_EMBED_STAGES
 #define B200WM_EMBED_STAGES 3
 #endif
@@ -55,16 +60,21 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Wait for the phase with the given parity.  The suspend-time hint lets the hardware park the warp
+// until the barrier completes (it is woken by the arrival) instead of spinning through issue slots.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "B200WM_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra B200WM_DONE;\n"
         "bra B200WM_WAIT;\n"
         "B200WM_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
 }
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0, 16-byte aligned)
 __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
@@ -116,79 +126,87 @@ __device__ __forceinline__ long long strip_offset(const Item& it, const StripGeo
     return it.frame * sg.frame_stride + (long long)it.ty * sg.strip_bytes;
 }
 
+// full[s]: armed by the producer with the byte count of a load into slot s, completed by the copy engine.
+// done[s]: one arrival per consumer warp when it has finished with slot s.
 template <int kStages>
-__device__ __forceinline__ void init_ring(unsigned bar0) {
+__device__ __forceinline__ void init_ring(unsigned full0, unsigned done0) {
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(done0 + 8 * s, kConsumerWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 }
 
+__device__ __forceinline__ void load_strip(const uint8_t* src, int i, unsigned slot, unsigned bar, const StripGeom& sg) {
+    mbar_arrive_expect_tx(bar, sg.strip_bytes);
+    bulk_load(slot, src + strip_offset(item_of(i, sg), sg), sg.strip_bytes, bar);
+}
+
 // ---- extract -------------------------------------------------------------------------------------------
 // raw_bits must be zero on entry (the launcher clears it): warps OR their bits in.
-__global__ void __launch_bounds__(kStripThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src, ExtractArgs ex,
-                                                                          StripGeom sg) {
+__global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src,
+                                                                                               ExtractArgs ex, StripGeom sg) {
     constexpr int kStages = kExtractStages;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) unsigned long long bars[kStages];
-    __shared__ int cta_counts[2][32];        // per-strip vote counts, double-buffered by iteration parity
+    __shared__ __align__(8) unsigned long long bars[2 * kStages];
+    __shared__ int cta_counts[kStages][32];          // per-strip vote counts, one buffer per ring slot
     const unsigned ring = smem_u32(smem);
-    const unsigned bar0 = smem_u32(&bars[0]);
-    const int lane = threadIdx.x & 31;
+    const unsigned full0 = smem_u32(&bars[0]), done0 = smem_u32(&bars[kStages]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TileGeom& g = sg.g;
-    if (threadIdx.x < 64) cta_counts[threadIdx.x >> 5][threadIdx.x & 31] = 0;
-    init_ring<kStages>(bar0);
-
+    if (threadIdx.x < kStages * 32) cta_counts[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+    init_ring<kStages>(full0, done0);
     const int step = (int)gridDim.x;
-    if (threadIdx.x == 0) {          // prologue: fill the ring
+    const int L = ex.payload_len;
+    int stage = 0;
+    unsigned parity = 0;
+
+    if (warp == kConsumerWarps) {
+        // ===== producer warp: loads, and the per-strip flush of the vote counters =====
+        if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            const int i = (int)blockIdx.x + s * step;
-            if (i < sg.total) {
-                mbar_arrive_expect_tx(bar0 + 8 * s, sg.strip_bytes);
-                bulk_load(ring + s * sg.strip_bytes, src + strip_offset(item_of(i, sg), sg), sg.strip_bytes, bar0 + 8 * s);
-            }
+            for (int s = 0; s < kStages; ++s)
+                if ((int)blockIdx.x + s * step < sg.total)
+                    load_strip(src, (int)blockIdx.x + s * step, ring + s * sg.strip_bytes, full0 + 8 * s, sg);
         }
+        for (int i = (int)blockIdx.x; i < sg.total; i += step) {
+            mbar_wait(done0 + 8 * stage, parity);        // every consumer warp is done with this slot
+            if (ex.pos_counts && lane < L) {
+                const int n = cta_counts[stage][lane];
+                if (n) {
+                    atomicAdd(&ex.pos_counts[(long long)item_of(i, sg).frame * L + lane], n);
+                    cta_counts[stage][lane] = 0;
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && i + kStages * step < sg.total)
+                load_strip(src, i + kStages * step, ring + stage * sg.strip_bytes, full0 + 8 * stage, sg);
+            if (++stage == kStages) { stage = 0; parity ^= 1u; }
+        }
+        return;
     }
 
-    int stage = 0, flip = 0;
-    unsigned parity = 0;
-    const int L = ex.payload_len;
+    // ===== consumer warps =====
     const int t = threadIdx.x;                       // one pass: the launcher guarantees tiles_x <= kStripThreads
     const bool live = t < g.tiles_x;
     const bool warp_live = (t & ~31) < g.tiles_x;    // warp-uniform
-    int prev_frame = -1;
-    for (int i = (int)blockIdx.x; i < sg.total; i += step, flip ^= 1) {
+    for (int i = (int)blockIdx.x; i < sg.total; i += step) {
         const Item it = item_of(i, sg);
         const unsigned slot = ring + stage * sg.strip_bytes;
-        mbar_wait(bar0 + 8 * stage, parity);
-        float S[16];
-        if (live) {
-            uint2 rows[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) rows[r] = lds_u2(slot + r * sg.pitch + t * 8);
-            sums_from_rows(rows, S);
-        }
-        // Early barrier: the warps arrive together (they all just waited on the same mbarrier) and the
-        // slot is handed back to the copy engine before the eigen-iteration, not after it.
-        __syncthreads();
-        if (t == 0 && i + kStages * step < sg.total) {     // refill with the strip kStages iterations ahead
-            mbar_arrive_expect_tx(bar0 + 8 * stage, sg.strip_bytes);
-            bulk_load(slot, src + strip_offset(item_of(i + kStages * step, sg), sg), sg.strip_bytes, bar0 + 8 * stage);
-        }
-        if (ex.pos_counts && t < L && prev_frame >= 0) {
-            // votes of the previous strip: complete since the barrier above; its buffer is reused two barriers from now
-            const int n = cta_counts[flip ^ 1][t];
-            if (n) {
-                atomicAdd(&ex.pos_counts[(long long)prev_frame * L + t], n);
-                cta_counts[flip ^ 1][t] = 0;
-            }
-        }
-        prev_frame = it.frame;
+        mbar_wait(full0 + 8 * stage, parity);
         int bit = 0;
         if (live) {
+            float S[16];
+            {
+                uint2 rows[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) rows[r] = lds_u2(slot + r * sg.pitch + t * 8);
+                sums_from_rows(rows, S);
+            }
             float sigma;
             bit = extract_bit(S, ex.scale, ex.inv_scale, sigma);
         }
@@ -204,53 +222,63 @@ __global__ void __launch_bounds__(kStripThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd
             if (ex.pos_counts && lane < L) {
                 // lane i sees the bits of blocks c0+i, c0+i+L, ...: payload position (c0 + i) mod L
                 const int n = __popc(ballot & (ex.every << lane));
-                if (n) atomicAdd(&cta_counts[flip][(c0 + lane) & (unsigned)(L - 1)], n);
+                if (n) atomicAdd(&cta_counts[stage][(c0 + lane) & (unsigned)(L - 1)], n);
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(done0 + 8 * stage);
         if (++stage == kStages) { stage = 0; parity ^= 1u; }
-    }
-    __syncthreads();
-    if (ex.pos_counts && t < L && prev_frame >= 0) {
-        const int n = cta_counts[flip ^ 1][t];
-        if (n) atomicAdd(&ex.pos_counts[(long long)prev_frame * L + t], n);
     }
 }
 
 // ---- embed ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                                        EmbedArgs em, StripGeom sg) {
+__global__ void __launch_bounds__(kCtaThreads) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                      EmbedArgs em, StripGeom sg) {
     constexpr int kStages = kEmbedStages;
     static_assert(kStages >= 3, "a slot is refilled one iteration after its store was committed");
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) unsigned long long bars[kStages];
+    __shared__ __align__(8) unsigned long long bars[2 * kStages];
     const unsigned ring = smem_u32(smem);
-    const unsigned bar0 = smem_u32(&bars[0]);
-    const int lane = threadIdx.x & 31;
+    const unsigned full0 = smem_u32(&bars[0]), done0 = smem_u32(&bars[kStages]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TileGeom& g = sg.g;
-    init_ring<kStages>(bar0);
-
+    init_ring<kStages>(full0, done0);
     const int step = (int)gridDim.x;
-    if (threadIdx.x == 0) {
+    int stage = 0;
+    unsigned parity = 0;
+
+    if (warp == kConsumerWarps) {
+        // ===== producer warp (one lane): loads, stores, refills =====
+        if (lane != 0) return;
 #pragma unroll
-        for (int s = 0; s < kStages - 1; ++s) {          // the last slot is filled by the first refill
-            const int i = (int)blockIdx.x + s * step;
-            if (i < sg.total) {
-                mbar_arrive_expect_tx(bar0 + 8 * s, sg.strip_bytes);
-                bulk_load(ring + s * sg.strip_bytes, src + strip_offset(item_of(i, sg), sg), sg.strip_bytes, bar0 + 8 * s);
-            }
+        for (int s = 0; s < kStages - 1; ++s)            // the last slot is filled by the first refill
+            if ((int)blockIdx.x + s * step < sg.total)
+                load_strip(src, (int)blockIdx.x + s * step, ring + s * sg.strip_bytes, full0 + 8 * s, sg);
+        int refill = kStages - 1;
+        for (int i = (int)blockIdx.x; i < sg.total; i += step) {
+            mbar_wait(done0 + 8 * stage, parity);        // every consumer warp has rewritten its tiles of this strip
+            bulk_store(dst + strip_offset(item_of(i, sg), sg), ring + stage * sg.strip_bytes, sg.strip_bytes);
+            bulk_commit();
+            // the slot stored one iteration ago has been read by now (at most this store pending)
+            bulk_wait_read<1>();
+            const int nxt = i + (kStages - 1) * step;    // the strip kStages-1 iterations ahead
+            if (nxt < sg.total) load_strip(src, nxt, ring + refill * sg.strip_bytes, full0 + 8 * refill, sg);
+            refill = stage;
+            if (++stage == kStages) { stage = 0; parity ^= 1u; }
         }
+        bulk_wait_read<0>();
+        return;
     }
 
-    int stage = 0, refill = kStages - 1;
-    unsigned parity = 0;
+    // ===== consumer warps =====
+    const int t = threadIdx.x;                           // one pass: the launcher guarantees tiles_x <= kStripThreads
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
         const Item it = item_of(i, sg);
         const unsigned slot = ring + stage * sg.strip_bytes;
-        // the 32 watermark bits of each warp's tiles, funnel-shifted out of two words of the packed
+        // the 32 watermark bits of this warp's tiles, funnel-shifted out of two words of the packed
         // row; issued before the wait so that their latency hides behind it
         const int row = em.frame_row ? em.frame_row[it.frame] : 0;
         const uint32_t* wrow = em.wm + (long long)row * em.wm_words;
-        const int t = threadIdx.x;                   // one pass: the launcher guarantees tiles_x <= kStripThreads
         const unsigned c0 = (unsigned)(it.ty * g.tiles_x + (t & ~31));
         const int wi = (int)(c0 >> 5);
         unsigned bits = 0u;
@@ -258,7 +286,7 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const u
             const unsigned lo = wrow[wi], hi = (wi + 1 < em.wm_words) ? wrow[wi + 1] : 0u;
             bits = __funnelshift_r(lo, hi, c0 & 31u);
         }
-        mbar_wait(bar0 + 8 * stage, parity);
+        mbar_wait(full0 + 8 * stage, parity);
         if (t < g.tiles_x) {
             const unsigned mine = slot + t * 8;
             float S[16], D[16];
@@ -270,34 +298,21 @@ __global__ void __launch_bounds__(kStripThreads) dwtsvd_embed_tma_kernel(const u
             }
             embed_deltas<false>(S, (bits >> lane) & 1u, em.scale, em.inv_scale, 12582912.0f, D, nullptr);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const unsigned d01 = __byte_perm(__float_as_uint(D[4 * i + 0]), __float_as_uint(D[4 * i + 1]), 0x5410);
-                const unsigned d23 = __byte_perm(__float_as_uint(D[4 * i + 2]), __float_as_uint(D[4 * i + 3]), 0x5410);
+            for (int i2 = 0; i2 < 4; ++i2) {
+                const unsigned d01 = __byte_perm(__float_as_uint(D[4 * i2 + 0]), __float_as_uint(D[4 * i2 + 1]), 0x5410);
+                const unsigned d23 = __byte_perm(__float_as_uint(D[4 * i2 + 2]), __float_as_uint(D[4 * i2 + 3]), 0x5410);
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const unsigned a = mine + (2 * i + rr) * sg.pitch;
+                    const unsigned a = mine + (2 * i2 + rr) * sg.pitch;
                     sts_u2(a, add_clamp_row(lds_u2(a), d01, d23));
                 }
             }
         }
-        fence_async_smem();          // generic-proxy writes -> visible to the bulk store
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            bulk_store(dst + strip_offset(it, sg), slot, sg.strip_bytes);
-            bulk_commit();
-            // the slot stored one iteration ago has been read by now (at most this store pending)
-            bulk_wait_read<1>();
-            const int nxt = i + (kStages - 1) * step;     // the strip kStages-1 iterations ahead
-            if (nxt < sg.total) {
-                mbar_arrive_expect_tx(bar0 + 8 * refill, sg.strip_bytes);
-                bulk_load(ring + refill * sg.strip_bytes, src + strip_offset(item_of(nxt, sg), sg), sg.strip_bytes,
-                          bar0 + 8 * refill);
-            }
-        }
-        refill = stage;
+        fence_async_smem();          // generic-proxy writes -> visible to the producer's bulk store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(done0 + 8 * stage);
         if (++stage == kStages) { stage = 0; parity ^= 1u; }
     }
-    if (threadIdx.x == 0) bulk_wait_read<0>();
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -323,7 +338,7 @@ static int persistent_grid(Kernel kernel, size_t smem, int* blocks) {
     }
     B200WM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    B200WM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStripThreads, smem));
+    B200WM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kCtaThreads, smem));
     if (per_sm < 1) per_sm = 1;
     *blocks = sms * per_sm;
     return B200WM_OK;
@@ -347,7 +362,7 @@ int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const Til
     if (rc) return rc;
     const long long strips = (long long)pl->n_frames * g.tiles_y;
     if (strips < blocks) blocks = (int)strips;
-    dwtsvd_extract_tma_kernel<<<blocks, kStripThreads, smem, stream>>>((const uint8_t*)src, xa, make_strip_geom(g, pl));
+    dwtsvd_extract_tma_kernel<<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, xa, make_strip_geom(g, pl));
     B200WM_LAUNCH_CHECK("dwtsvd_extract_tma_kernel");
     return B200WM_OK;
 }
@@ -360,7 +375,7 @@ int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, 
     if (rc) return rc;
     const long long strips = (long long)pl->n_frames * g.tiles_y;
     if (strips < blocks) blocks = (int)strips;
-    dwtsvd_embed_tma_kernel<<<blocks, kStripThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea,
+    dwtsvd_embed_tma_kernel<<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea,
                                                                      make_strip_geom(g, pl));
     B200WM_LAUNCH_CHECK("dwtsvd_embed_tma_kernel");
     return B200WM_OK;
