@@ -258,6 +258,16 @@ B200WM_API int b200wm_dwtsvd_detect_host(const uint8_t* src_host, const b200wm_p
 B200WM_API int b200wm_attack_jpeg_requant(const void* src, void* dst, const b200wm_plane* plane, int32_t quality, void* stream);
 /* x + noise (float32 [n_frames, height, width], contiguous), round, clip.  dst may equal src. */
 B200WM_API int b200wm_attack_add_noise(const void* src, void* dst, const b200wm_plane* plane, const float* noise, void* stream);
+/*
+ * cv2.resize of planar uint8 planes, bit for bit as OpenCV 4.x computes it on uint8: INTER_AREA
+ * (reductions only: float cell weights, or integer sums for whole-number ratios) and INTER_LINEAR
+ * (11-bit fixed-point weights).  Same n_frames on both sides; src and dst must not overlap.
+ * The resize attack of config 5 is AREA 1080p -> 720p followed by LINEAR 720p -> 1080p.
+ */
+#define B200WM_INTER_LINEAR 1   /* cv2.INTER_LINEAR */
+#define B200WM_INTER_AREA 3     /* cv2.INTER_AREA */
+B200WM_API int b200wm_attack_resize(const void* src, const b200wm_plane* src_plane, void* dst, const b200wm_plane* dst_plane,
+                        int32_t interpolation, void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,11 +66,16 @@ def main():
             m = min(100, n - f0)
             ops.attack_add_noise_(work[f0:f0 + m], sigma * torch.randn((m, H, W), device=dev, generator=g))
 
+    def resize():
+        for f0 in range(0, n, 500):
+            ops.attack_resize_roundtrip_(work[f0:f0 + 500])
+
     attacks = [("none", lambda: None), ("jpeg-like q95", lambda: ops.attack_jpeg_requant_(work, 95)),
                ("jpeg-like q85", lambda: ops.attack_jpeg_requant_(work, 85)),
                ("jpeg-like q75", lambda: ops.attack_jpeg_requant_(work, 75)),
                ("gaussian sigma 1", lambda: noise(1.0)), ("gaussian sigma 2", lambda: noise(2.0)),
-               ("gaussian sigma 4", lambda: noise(4.0))]
+               ("gaussian sigma 4", lambda: noise(4.0)),
+               ("resize 1080p-720p-1080p (area, bilinear)", lambda: resize())]
     rows = []
     for name, attack in attacks:
         work.copy_(marked)

@@ -86,3 +86,44 @@ def test_gpu_attack_kernels_match_cpu_definitions(marked_frames):
         ref_bits = o_svd.extract_plane(got)[0]
         edge, _, _ = knife_edge_blocks(got.astype(np.float32))
         assert all(edge[c] for c in np.flatnonzero(bits != ref_bits))
+
+
+@pytest.mark.parametrize("src_hw,dst_hw", [((1080, 1920), (720, 1280)), ((240, 320), (160, 213)), ((64, 96), (48, 40)),
+                                           ((37, 53), (20, 31)), ((48, 96), (24, 48)), ((48, 96), (16, 32)),
+                                           ((48, 96), (24, 32)), ((30, 50), (30, 25)), ((9, 11), (1, 1))])
+def test_gpu_resize_is_cv2_bit_for_bit(src_hw, dst_hw):
+    """b200wm_attack_resize == cv2.resize on uint8 planes, INTER_AREA down and INTER_LINEAR both ways,
+    batched, with a pitched (non-contiguous) source."""
+    import cv2
+    from b200wm import ops
+    rng = np.random.RandomState(src_hw[1] + dst_hw[0])
+    frames = rng.randint(0, 256, (3,) + src_hw + (2,)).astype(np.uint8)
+    src = frames[..., 0]
+    dsize = (dst_hw[1], dst_hw[0])
+    t = torch.from_numpy(frames).to(DEV)[..., 0].permute(0, 1, 2)       # element stride 2 is not planar:
+    t = t.contiguous()[:, :, :]                                          # planar copy ...
+    pad = torch.zeros((3, src_hw[0], src_hw[1] + 5), dtype=torch.uint8, device=DEV)
+    pad[:, :, :src_hw[1]] = t                                            # ... inside wider rows (pitch != width)
+    view = pad[:, :, :src_hw[1]]
+    small = ops.attack_resize(view, dsize, ops.INTER_AREA)
+    for f in range(3):
+        assert np.array_equal(small[f].cpu().numpy(), cv2.resize(src[f], dsize, interpolation=cv2.INTER_AREA)), f
+    back = ops.attack_resize(small, (src_hw[1], src_hw[0]), ops.INTER_LINEAR)
+    down = ops.attack_resize(view, dsize, ops.INTER_LINEAR)
+    for f in range(3):
+        want_small = cv2.resize(src[f], dsize, interpolation=cv2.INTER_AREA)
+        assert np.array_equal(back[f].cpu().numpy(), cv2.resize(want_small, (src_hw[1], src_hw[0]), interpolation=cv2.INTER_LINEAR))
+        assert np.array_equal(down[f].cpu().numpy(), cv2.resize(src[f], dsize, interpolation=cv2.INTER_LINEAR))
+
+
+def test_gpu_resize_roundtrip_and_errors(marked_frames):
+    from b200wm import ops
+    marked, _ = marked_frames
+    t = torch.from_numpy(marked.copy()).to(DEV)
+    ops.attack_resize_roundtrip_(t)
+    for f in range(marked.shape[0]):
+        assert np.array_equal(t[f].cpu().numpy(), attacks.resize_roundtrip(marked[f]))
+    with pytest.raises(Exception):        # INTER_AREA enlargement is a different filter in OpenCV: refused
+        ops.attack_resize(t, (W * 2, H * 2), ops.INTER_AREA)
+    with pytest.raises(Exception):
+        ops.attack_resize(t, (W // 2, H // 2), 2)    # INTER_CUBIC

@@ -4,6 +4,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from oracle import bracket, dct8, dwt_dct_svd as svd, haar, payload, synth
 from parity import PAYLOAD, KEY
@@ -142,3 +143,23 @@ def test_u8_plane_1080p(golden_dir):
     assert hashlib.sha256(y.tobytes()).hexdigest() == str(g["src_sha256"])
     bits = svd.extract_plane(y)
     assert np.array_equal(bits, _bits(g["bits_clean"], bits.size))
+
+
+RESIZE_CASES = [((1080, 1920), (720, 1280)), ((240, 320), (160, 213)), ((64, 96), (48, 40)), ((37, 53), (20, 31)),
+                ((48, 96), (24, 48)), ((48, 96), (16, 32)), ((48, 96), (24, 32)), ((30, 50), (30, 25)), ((9, 11), (1, 1))]
+
+
+@pytest.mark.parametrize("src_hw,dst_hw", RESIZE_CASES)
+def test_resize_restatement_is_cv2_bit_for_bit(src_hw, dst_hw):
+    """The step-by-step restatement of cv2.resize that csrc/attacks.cu follows equals OpenCV itself."""
+    import cv2
+    from oracle import attacks
+    rng = np.random.RandomState(src_hw[0] * 7 + dst_hw[1])
+    src = rng.randint(0, 256, src_hw).astype(np.uint8)
+    dsize = (dst_hw[1], dst_hw[0])
+    small = cv2.resize(src, dsize, interpolation=cv2.INTER_AREA)
+    assert np.array_equal(attacks.resize_area_restated(src, dsize), small)
+    back = cv2.resize(small, (src_hw[1], src_hw[0]), interpolation=cv2.INTER_LINEAR)
+    assert np.array_equal(attacks.resize_linear_restated(small, (src_hw[1], src_hw[0])), back)
+    # bilinear reductions too (the kernel is not limited to enlarging)
+    assert np.array_equal(attacks.resize_linear_restated(src, dsize), cv2.resize(src, dsize, interpolation=cv2.INTER_LINEAR))

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "b200wm_dwtsvd_detect_host": (C.c_int, [_vp, _PP, _f32, _i32, _vp, _vp, _vp, _vp, _i32]),
     "b200wm_attack_jpeg_requant": (C.c_int, [_vp, _vp, _PP, _i32, _vp]),
     "b200wm_attack_add_noise": (C.c_int, [_vp, _vp, _PP, _vp, _vp]),
+    "b200wm_attack_resize": (C.c_int, [_vp, _PP, _vp, _PP, _i32, _vp]),
 }
 
 

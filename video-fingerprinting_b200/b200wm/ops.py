@@ -360,6 +360,32 @@ def attack_add_noise_(planes, noise):
     return planes
 
 
+INTER_LINEAR, INTER_AREA = 1, 3      # cv2's values
+
+
+def attack_resize(planes, size, interpolation):
+    """cv2.resize(plane, (width, height), interpolation=...) for every uint8 plane of ``[N, H, W]``;
+    ``size`` is (width, height) like cv2's dsize.  Returns a new tensor."""
+    require_cuda()
+    v, pl = describe(planes)
+    dw, dh = int(size[0]), int(size[1])
+    out = _empty((v.shape[0], dh, dw), torch.uint8, v.device)
+    _, dpl = describe(out)
+    check(lib.b200wm_attack_resize(_ptr(v), C.byref(pl), _ptr(out), C.byref(dpl), int(interpolation), _stream()))
+    return out if planes.dim() == 3 else out[0]
+
+
+def attack_resize_roundtrip_(planes, scale=2.0 / 3.0):
+    """In place: INTER_AREA down by ``scale`` then INTER_LINEAR back (oracle/attacks.py:resize_roundtrip)."""
+    v, _ = describe(planes)
+    h, w = v.shape[1], v.shape[2]
+    small = attack_resize(v, (int(round(w * scale)), int(round(h * scale))), INTER_AREA)
+    _, pl = describe(small)
+    _, dpl = describe(v)
+    check(lib.b200wm_attack_resize(_ptr(small), C.byref(pl), _ptr(v), C.byref(dpl), INTER_LINEAR, _stream()))
+    return planes
+
+
 def set_path(path):
     """0 = automatic (TMA-staged kernels when the planes qualify), 1 = vectorised-load kernels only."""
     check(lib.b200wm_set_path(int(path)))

@@ -26,6 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fvisibility=hidden",
     "-fmad=false",     # no implicit contraction: every FMA is written as fmaf, so all kernel families round identically
     "-cudart", "static",
+    "--threads", "0",  # one compilation per source file in parallel
 ]
 
 

@@ -29,6 +29,7 @@ int launch_dct8_extract(const void*, const b200wm_plane*, const float*, const fl
 int launch_bgr8_to_yuv32(const uint8_t*, float*, long long, cudaStream_t);
 int launch_attack_jpeg(const void*, void*, const b200wm_plane*, int, cudaStream_t);
 int launch_attack_noise(const void*, void*, const b200wm_plane*, const float*, cudaStream_t);
+int launch_attack_resize(const void*, const b200wm_plane*, void*, const b200wm_plane*, int, cudaStream_t);
 int launch_embed_rgb8(const uint8_t*, uint8_t*, int, int, int, long long, long long, const float*, const uint32_t*, int, long long,
                       const int32_t*, cudaStream_t);
 int launch_extract_rgb8(const uint8_t*, int, int, int, long long, long long, int, float, uint32_t*, int, int, int32_t*, cudaStream_t);
@@ -162,6 +163,11 @@ B200WM_API int b200wm_attack_jpeg_requant(const void* src, void* dst, const b200
 
 B200WM_API int b200wm_attack_add_noise(const void* src, void* dst, const b200wm_plane* plane, const float* noise, void* stream) {
     return launch_attack_noise(src, dst, plane, noise, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_attack_resize(const void* src, const b200wm_plane* src_plane, void* dst, const b200wm_plane* dst_plane,
+                        int32_t interpolation, void* stream) {
+    return launch_attack_resize(src, src_plane, dst, dst_plane, interpolation, (cudaStream_t)stream);
 }
 
 B200WM_API int b200wm_dwtsvd_embed_rgb8(const uint8_t* src, uint8_t* dst, int32_t n_frames, int32_t height, int32_t width,
