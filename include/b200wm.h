@@ -125,6 +125,20 @@ B200WM_API int b200wm_dwtsvd_embed(const void* src, void* dst, const b200wm_plan
                         const int32_t* frame_wm_row, float scale, void* stream);
 
 /*
+ * One read, N marked copies of every frame: the "N watermarked copies of each segment" step of the
+ * reference's fingerprinting flow (tests/mark_video_to_hls.py:330-354 runs the embedder once per copy
+ * over the same source; payload = 4-bit segment || 4-bit copy, :27-43).  Copy c of frame f is written
+ * at dst + c*copy_stride_bytes + f*plane->frame_stride_bytes with the pitch of `plane`, carries
+ * watermark row copy_wm_row[f*n_copies + c] (NULL -> row c) and is bit-identical to
+ * b200wm_dwtsvd_embed with that row.  dst must not overlap src and must already hold whatever the
+ * caller wants outside the walked tiles (plane edges not covered by 8x8 tiles are not written).
+ * uint8 planes only.  Algorithmic bytes per frame: (1 + n_copies) * W * H.
+ */
+B200WM_API int b200wm_dwtsvd_embed_copies(const void* src, const b200wm_plane* plane, void* dst, int64_t copy_stride_bytes,
+                              int32_t n_copies, const uint32_t* wm_packed, int32_t n_wm_rows, int32_t wm_words,
+                              int64_t wm_len, const int32_t* copy_wm_row, float scale, void* stream);
+
+/*
  * Replaces DwtDctSvdDecoder.decode for one channel (extract/dwt_dct_svd_decoder.py:12-37:
  * bit = (sigma_0 % scale) > scale/2 per block) and the counting half of
  * DeShuffler.degenerate (degenerator/de_shuffler.py:17-18).

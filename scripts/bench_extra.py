@@ -99,6 +99,21 @@ def main():
     # ---- attack kernels
     y = planes(512, h, w)
     report("jpeg-like requant q75 (in place)", timed(lambda: ops.attack_jpeg_requant_(y, 75)), 512, 2 * h * w)
+    small = ops.attack_resize(y, (1280, 720), ops.INTER_AREA)
+    report("resize area 1080p -> 720p", timed(lambda: ops.attack_resize(y, (1280, 720), ops.INTER_AREA)), 512, h * w + 1280 * 720)
+    report("resize bilinear 720p -> 1080p", timed(lambda: ops.attack_resize(small, (w, h), ops.INTER_LINEAR)), 512, h * w + 1280 * 720)
+    del small
+    # ---- one read, N marked copies (fingerprinting flow): (1 + N) * W * H bytes per frame
+    y = y[:384]
+    for copies in (2, 4, 8):
+        rows = np.stack([Shuffler(key=0).generate_wm(np.array([int(b) for b in format(c, "08b")]), (1, h * w // 64))[0] for c in range(copies)])
+        wmc, lnc = ops.pack_bits(rows, device=DEV)
+        out = torch.empty((copies,) + tuple(y.shape), dtype=torch.uint8, device=DEV)
+        ms_c = timed(lambda: ops.dwtsvd_embed_copies(y, wmc, lnc, copies, out=out))
+        tmp = out[0]
+        ms_1 = timed(lambda: [ops.dwtsvd_embed_(y, wmc, lnc, out=tmp, frame_wm_row=None) for _ in range(copies)])
+        report(f"{copies} marked copies, one read", ms_c, y.shape[0], (1 + copies) * h * w, single_embeds_ms=round(ms_1, 4))
+        del out
 
 
 if __name__ == "__main__":

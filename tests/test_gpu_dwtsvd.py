@@ -317,3 +317,45 @@ def test_random_geometries_both_paths_agree():
             for a, b in zip(outs[0], other):
                 assert np.array_equal(a, b), (case, n, h, w)
     ops.set_path(0)
+
+
+@pytest.mark.parametrize("h,w,pad", [(1080, 1920, 0), (240, 320, 0), (70, 90, 3), (37, 53, 0)])
+def test_multi_copy_embed_equals_single_embeds(h, w, pad):
+    """b200wm_dwtsvd_embed_copies: one read, N marked copies (tests/mark_video_to_hls.py:330-354), each
+    bit-identical to a single embed of its payload row - with per-(frame, copy) row tables, pitched
+    planes (generic path) and tile-uncovered edges - and every copy's payload decodes."""
+    from b200wm import ops
+    DEV = _dev()
+    n_frames, n_copies = 3, 4
+    rng = np.random.RandomState(h + w)
+    frames = rng.randint(0, 256, (n_frames, h, w + pad)).astype(np.uint8)
+    frames[0, :16, :32] = 0           # all-zero blocks
+    frames[1, :8, :8] = 255
+    src = torch.from_numpy(frames).to(DEV)[:, :, :w]
+    n = h * w // 64
+    payloads = [o_pay.payload_for_segment_copy(s, c) for s in range(2) for c in range(n_copies)]
+    wm = np.stack([o_pay.generate_wm(p, (1, n), KEY)[0] for p in payloads])
+    packed, ln = ops.pack_bits(wm, device=DEV)
+    # frame f belongs to segment f % 2: row = segment * n_copies + copy
+    table = torch.tensor([[(f % 2) * n_copies + c for c in range(n_copies)] for f in range(n_frames)], dtype=torch.int32, device=DEV)
+    out = ops.dwtsvd_embed_copies(src, packed, ln, n_copies, copy_wm_row=table)
+    assert out.shape == (n_copies, n_frames, h, w)
+    for c in range(n_copies):
+        single = src.clone()
+        ops.dwtsvd_embed_(single, packed, ln, frame_wm_row=table[:, c].contiguous())
+        assert torch.equal(out[c], single), f"copy {c} differs from a single embed"
+        raw, counts = ops.dwtsvd_extract(out[c], payload_len=8)
+        perm = torch.from_numpy(o_pay.permutation(8, KEY).astype(np.int32)).to(DEV)
+        patterns, _ = ops.vote_finish(counts, n, perm)
+        if h >= 240:
+            for f in range(n_frames):
+                assert np.array_equal(patterns[f].cpu().numpy(), payloads[(f % 2) * n_copies + c])
+    # default table: row c for every frame
+    out2 = ops.dwtsvd_embed_copies(src, packed, ln, 2)
+    for c in range(2):
+        single = src.clone()
+        ops.dwtsvd_embed_(single, packed, ln, frame_wm_row=torch.full((n_frames,), c, dtype=torch.int32, device=DEV))
+        assert torch.equal(out2[c], single)
+    if n > 32:
+        with pytest.raises(IndexError):          # watermark shorter than the block count, as embed/dwt_dct_svd_encoder.py:36
+            ops.dwtsvd_embed_copies(src, packed[:, :1].contiguous(), 32, 2)

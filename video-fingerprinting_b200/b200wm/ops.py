@@ -131,6 +131,42 @@ def dwtsvd_embed_(planes, wm_packed, wm_len, scale=15.0, channel=None, frame_wm_
     return dst_t
 
 
+def dwtsvd_embed_copies(planes, wm_packed, wm_len, n_copies, scale=15.0, copy_wm_row=None, out=None):
+    """One read, ``n_copies`` marked copies of every uint8 plane (tests/mark_video_to_hls.py:330-354).
+
+    ``out`` (optional) is a uint8 tensor ``[n_copies, N, ...]`` whose slices ``out[c]`` have the strides of
+    ``planes``; by default it is allocated and pre-filled with the source so that samples outside the
+    walked tiles (edges not covered by 8x8 tiles, chroma planes of an I420 buffer) are copies too.
+    Copy ``c`` of frame ``f`` carries watermark row ``copy_wm_row[f, c]`` (default: row ``c``)."""
+    require_cuda()
+    v, pl = describe(planes)
+    if v.dtype != torch.uint8:
+        raise ValueError("multi-copy embed takes uint8 planes")
+    if wm_packed.dtype != torch.int32 or wm_packed.dim() != 2 or not wm_packed.is_contiguous() or not wm_packed.is_cuda:
+        raise ValueError("wm_packed must be a contiguous CUDA int32 [rows, words] tensor (see pack_bits)")
+    n_copies = int(n_copies)
+    if out is None:
+        # same strides as the source inside each copy (the library addresses copy c with the source's pitches)
+        extent = sum((d - 1) * st for d, st in zip(planes.shape, planes.stride())) + 1
+        out = torch.empty_strided((n_copies,) + tuple(planes.shape), ((extent + 15) // 16 * 16,) + tuple(planes.stride()),
+                                  dtype=torch.uint8, device=planes.device)
+        out.copy_(planes.unsqueeze(0).expand_as(out))
+    if out.dtype != torch.uint8 or not out.is_cuda or out.shape[0] != n_copies or out.dim() != planes.dim() + 1:
+        raise ValueError("out must be a CUDA uint8 tensor [n_copies, *planes.shape]")
+    if n_copies:
+        ov, opl = describe(out[0])
+        if (opl.pitch_bytes, opl.frame_stride_bytes, opl.elem_stride, opl.height, opl.width, opl.n_frames) != \
+                (pl.pitch_bytes, pl.frame_stride_bytes, pl.elem_stride, pl.height, pl.width, pl.n_frames):
+            raise ValueError("every out[c] must have the geometry (strides included) of planes")
+    if copy_wm_row is not None and (copy_wm_row.dtype != torch.int32 or tuple(copy_wm_row.shape) != (pl.n_frames, n_copies)
+                                    or not copy_wm_row.is_cuda or not copy_wm_row.is_contiguous()):
+        raise ValueError("copy_wm_row must be a contiguous CUDA int32 [n_frames, n_copies] tensor")
+    check(lib.b200wm_dwtsvd_embed_copies(_ptr(v), C.byref(pl), _ptr(out), int(out.stride(0)) if n_copies else 0, n_copies,
+                                         _ptr(wm_packed), wm_packed.shape[0], wm_packed.shape[1], int(wm_len),
+                                         _ptr(copy_wm_row), float(scale), _stream()))
+    return out
+
+
 def dwtsvd_extract(planes, scale=15.0, payload_len=None, channel=None, raw_bits=None, pos_counts=None):
     """-> (raw_bits int32 [N, words], pos_counts int32 [N, payload_len] or None)."""
     require_cuda()

@@ -28,6 +28,8 @@ int launch_dct8_extract(const void*, const b200wm_plane*, const float*, const fl
                         int, int32_t*, cudaStream_t);
 int launch_bgr8_to_yuv32(const uint8_t*, float*, long long, cudaStream_t);
 int launch_attack_jpeg(const void*, void*, const b200wm_plane*, int, cudaStream_t);
+int launch_dwtsvd_embed_copies(const void*, const b200wm_plane*, void*, long long, int, const uint32_t*, int, int, long long,
+                               const int32_t*, float, cudaStream_t);
 int launch_attack_noise(const void*, void*, const b200wm_plane*, const float*, cudaStream_t);
 int launch_attack_resize(const void*, const b200wm_plane*, void*, const b200wm_plane*, int, cudaStream_t);
 int launch_embed_rgb8(const uint8_t*, uint8_t*, int, int, int, long long, long long, const float*, const uint32_t*, int, long long,
@@ -93,6 +95,13 @@ B200WM_API int32_t b200wm_words_per_frame(int height, int width) {
 B200WM_API int b200wm_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* plane, const uint32_t* wm_packed,
                         int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, float scale, void* stream) {
     return launch_dwtsvd_embed(src, dst, plane, wm_packed, wm_words, wm_len, frame_wm_row, scale, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_dwtsvd_embed_copies(const void* src, const b200wm_plane* plane, void* dst, int64_t copy_stride_bytes,
+                              int32_t n_copies, const uint32_t* wm_packed, int32_t n_wm_rows, int32_t wm_words,
+                              int64_t wm_len, const int32_t* copy_wm_row, float scale, void* stream) {
+    return launch_dwtsvd_embed_copies(src, plane, dst, copy_stride_bytes, n_copies, wm_packed, n_wm_rows, wm_words, wm_len,
+                                      copy_wm_row, scale, (cudaStream_t)stream);
 }
 
 B200WM_API int b200wm_dwtsvd_extract(const void* src, const b200wm_plane* plane, float scale, uint32_t* raw_bits,

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "svd4.cuh"
+#include "svd4x2.cuh"
 
 namespace b200wm {
 
@@ -154,6 +155,41 @@ __device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scal
     }
 }
 
+// The bit-independent half of the quantisation, for callers that embed SEVERAL payloads into the same
+// block (one read, N marked copies): sigma_0, the floor quotient, v0 and S v0.  embed_copy_deltas()
+// then repeats, bit by bit, exactly the arithmetic of embed_deltas() above, so copy c of a multi-copy
+// embed is bit-identical to a single embed of payload c.
+struct BlockPair {
+    float sigma, q;      // sigma_0 of the LL block and floor(sigma_0 / scale)
+    float v[4], sv[4];   // right singular vector and S v (per LL row)
+    bool zero;
+};
+
+__device__ __forceinline__ void embed_prepare(const float (&S)[16], float scale, float inv_scale, BlockPair& bp) {
+    bp.sigma = 0.5f * top_singular<true>(S, bp.v, bp.zero);
+    float rem;
+    floor_divmod(bp.sigma, scale, inv_scale, bp.q, rem);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        bp.sv[i] = fmaf(S[4 * i + 3], bp.v[3], fmaf(S[4 * i + 2], bp.v[2], fmaf(S[4 * i + 1], bp.v[1], S[4 * i] * bp.v[0])));
+}
+
+__device__ __forceinline__ void embed_copy_deltas(const BlockPair& bp, int bit, float scale, float bias, float (&D)[16]) {
+    const float target = (bp.q + 0.25f + 0.5f * (float)bit) * scale;
+    if (bp.zero) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) D[k] = fmaf(target, 0.125f, bias);
+        return;
+    }
+    const float t = 0.25f * ((target - bp.sigma) / bp.sigma);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = t * bp.sv[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) D[4 * i + j] = fmaf(a, bp.v[j], bias);
+    }
+}
+
 __device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, float inv_scale, float& sigma) {
     float v[4];
     bool zero;
@@ -163,5 +199,76 @@ __device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, fl
     return rem > 0.5f * scale ? 1 : 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// two tiles per thread, packed FP32 (svd4x2.cuh); lane .x = first tile, lane .y = second tile
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sums_from_rows_x2(const uint2 (&ra)[8], const uint2 (&rb)[8], f2 (&S)[16]) {
+    constexpr unsigned kMagic = 0x4B000000u;
+    const f2 minus_magic = bc2(-8388608.0f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        unsigned sa[4], sb[4];
+        {
+            const uint2 a = ra[2 * i], b = ra[2 * i + 1];
+            sa[0] = __dp4a(b.x, 0x00000101u, __dp4a(a.x, 0x00000101u, kMagic));
+            sa[1] = __dp4a(b.x, 0x01010000u, __dp4a(a.x, 0x01010000u, kMagic));
+            sa[2] = __dp4a(b.y, 0x00000101u, __dp4a(a.y, 0x00000101u, kMagic));
+            sa[3] = __dp4a(b.y, 0x01010000u, __dp4a(a.y, 0x01010000u, kMagic));
+        }
+        {
+            const uint2 a = rb[2 * i], b = rb[2 * i + 1];
+            sb[0] = __dp4a(b.x, 0x00000101u, __dp4a(a.x, 0x00000101u, kMagic));
+            sb[1] = __dp4a(b.x, 0x01010000u, __dp4a(a.x, 0x01010000u, kMagic));
+            sb[2] = __dp4a(b.y, 0x00000101u, __dp4a(a.y, 0x00000101u, kMagic));
+            sb[3] = __dp4a(b.y, 0x01010000u, __dp4a(a.y, 0x01010000u, kMagic));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            S[4 * i + j] = add2(make_float2(__uint_as_float(sa[j]), __uint_as_float(sb[j])), minus_magic);
+    }
+}
+
+// extract_bit() for both lanes: bit 0 = first tile, bit 1 = second tile
+__device__ __forceinline__ unsigned extract_bits_x2(const f2 (&S)[16], float scale, float inv_scale) {
+    f2 v[4];
+    const Pair2 p = top_singular_x2<false>(S, v);
+    const f2 sigma = mul2(bc2(0.5f), p.sigma0);
+    f2 q, rem;
+    floor_divmod2(sigma, scale, inv_scale, q, rem);
+    const float half = 0.5f * scale;
+    return (rem.x > half ? 1u : 0u) | (rem.y > half ? 2u : 0u);
+}
+
+// embed_deltas() for both lanes (bits: bit 0 = first tile, bit 1 = second tile)
+__device__ __forceinline__ void embed_deltas_x2(const f2 (&S)[16], unsigned bits, float scale, float inv_scale, float bias,
+                                                f2 (&D)[16]) {
+    f2 v[4];
+    const Pair2 p = top_singular_x2<true>(S, v);
+    const f2 sigma = mul2(bc2(0.5f), p.sigma0);
+    f2 q, rem;
+    floor_divmod2(sigma, scale, inv_scale, q, rem);
+    const f2 bit = make_float2((float)(bits & 1u), (float)((bits >> 1) & 1u));
+    const f2 target = mul2(add2(add2(q, bc2(0.25f)), mul2(bc2(0.5f), bit)), bc2(scale));
+    const f2 diff = add2(target, neg2(sigma));
+    const f2 t = mul2(bc2(0.25f), make_float2(diff.x / sigma.x, diff.y / sigma.y));
+    const f2 bias2 = bc2(bias);
+    // svd(0) = (I, 0, I): an all-zero block gets the flat increment target/8 on every sample
+    // (fmaf(target, 0.125f, bias) in the scalar code).  target/8 is exact, so the same value comes out
+    // of the common formula fma(a, v, bias) with a = target/8 and v = 1 on that lane.
+    const f2 flat = mul2(target, bc2(0.125f));
+    if (p.zero_x | p.zero_y) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = make_float2(p.zero_x ? 1.0f : v[j].x, p.zero_y ? 1.0f : v[j].y);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const f2 sv = fma2(S[4 * i + 3], v[3], fma2(S[4 * i + 2], v[2], fma2(S[4 * i + 1], v[1], mul2(S[4 * i], v[0]))));
+        f2 a = mul2(t, sv);
+        a = make_float2(p.zero_x ? flat.x : a.x, p.zero_y ? flat.y : a.y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) D[4 * i + j] = fma2(a, v[j], bias2);
+    }
+}
 
 }  // namespace b200wm

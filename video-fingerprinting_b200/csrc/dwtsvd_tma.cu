@@ -17,7 +17,9 @@
 //     (no CTA-wide barrier in the loop).  HBM latency is hidden by the ring depth, no consumer
 //     spends issue slots on global address arithmetic and the 64 source bytes of a tile never
 //     occupy registers for the length of the SVD.
-//   * Thread t owns tile t of the strip: it reads its 8x8 bytes from shared memory
+//   * Consumer thread t owns TWO tiles of the strip, t and t + 128, and runs the eigen-iteration for
+//     both in packed FP32 (FFMA2/FMUL2/FADD2, svd4x2.cuh): the kernels are issue-bound, and a packed
+//     instruction does the work of two for one issue slot.  It reads its 8x8 bytes from shared memory
 //     (conflict-free: a warp reads 256 contiguous bytes per row).  Embed updates the strip in
 //     shared memory and writes it back with a bulk store (cp.async.bulk ... bulk_group); a slot
 //     is refilled one iteration after its store was committed
@@ -28,7 +30,7 @@
 //     and the embed kernel funnel-shifts its 32 watermark bits out of two words.
 //
 // Requirements (otherwise the launcher uses the vectorised-load kernels): planar uint8 with
-// tight rows (pitch == width), width a multiple of 16 between 512 and 2048 (one tile per thread,
+// tight rows (pitch == width), width a multiple of 16 between 512 and 2048 (two tiles per thread,
 // three strips per CTA and four CTAs per SM), base and frame stride multiples of 16 bytes.
 #include "common.cuh"
 #include "svd4.cuh"
@@ -36,7 +38,8 @@
 
 namespace b200wm {
 
-constexpr int kStripThreads = 256;                 // consumer threads: one 8x8 tile each
+constexpr int kStripThreads = 128;                 // consumer threads: two 8x8 tiles each (t and t + 128)
+constexpr int kMaxStripTiles = 2 * kStripThreads;
 constexpr int kConsumerWarps = kStripThreads / 32;
 constexpr int kCtaThreads = kStripThreads + 32;    // + the producer warp
 #ifndef B200WM_EMBED_STAGES
@@ -48,6 +51,9 @@ constexpr int kEmbedStages = B200WM_EMBED_STAGES;      // >= 3: load in flight +
 #endif
 #ifndef B200WM_EXTRACT_MIN_CTAS
 #define B200WM_EXTRACT_MIN_CTAS 4
+#endif
+#ifndef B200WM_EMBED_MIN_CTAS
+#define B200WM_EMBED_MIN_CTAS 3
 #endif
 constexpr int kExtractStages = B200WM_EXTRACT_STAGES;
 
@@ -98,6 +104,15 @@ __device__ __forceinline__ uint2 lds_u2(unsigned addr) {
 }
 __device__ __forceinline__ void sts_u2(unsigned addr, uint2 v) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+// predicated store: no branch (and no reconvergence bookkeeping) around the 16 row stores of a tile
+__device__ __forceinline__ void sts_u2_if(bool pred, unsigned addr, uint2 v) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %3, 0;\n"
+        "@p st.shared.v2.u32 [%0], {%1, %2};\n"
+        "}\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"((unsigned)pred) : "memory");
 }
 
 // ---- work items ---------------------------------------------------------------------------------------
@@ -191,39 +206,49 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
     }
 
     // ===== consumer warps =====
-    const int t = threadIdx.x;                       // one pass: the launcher guarantees tiles_x <= kStripThreads
-    const bool live = t < g.tiles_x;
-    const bool warp_live = (t & ~31) < g.tiles_x;    // warp-uniform
+    const int t = threadIdx.x, t_hi = t + kStripThreads;        // the launcher guarantees tiles_x <= 2 * kStripThreads
+    const bool live_lo = t < g.tiles_x, live_hi = t_hi < g.tiles_x;
+    const bool warp_live_lo = (t & ~31) < g.tiles_x, warp_live_hi = (t_hi & ~31) < g.tiles_x;     // warp-uniform
+    const unsigned off_lo = (live_lo ? t : 0) * 8, off_hi = (live_hi ? t_hi : 0) * 8;             // dead lanes read tile 0
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
         const Item it = item_of(i, sg);
         const unsigned slot = ring + stage * sg.strip_bytes;
         mbar_wait(full0 + 8 * stage, parity);
-        int bit = 0;
-        if (live) {
-            float S[16];
+        unsigned bits;
+        {
+            f2 S[16];
             {
-                uint2 rows[8];
+                uint2 ra[8], rb[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) rows[r] = lds_u2(slot + r * sg.pitch + t * 8);
-                sums_from_rows(rows, S);
+                for (int r = 0; r < 8; ++r) {
+                    ra[r] = lds_u2(slot + r * sg.pitch + off_lo);
+                    rb[r] = lds_u2(slot + r * sg.pitch + off_hi);
+                }
+                sums_from_rows_x2(ra, rb, S);
             }
-            float sigma;
-            bit = extract_bit(S, ex.scale, ex.inv_scale, sigma);
+            bits = extract_bits_x2(S, ex.scale, ex.inv_scale);
         }
-        if (warp_live) {
-            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
-            const unsigned c0 = (unsigned)(it.ty * g.tiles_x + (t & ~31));
-            const unsigned sh = c0 & 31u;
-            if (lane == 0 && ballot) {
-                uint32_t* w = ex.raw_bits + (long long)it.frame * g.words + (c0 >> 5);
-                atomicOr(w, ballot << sh);
-                if (sh && (ballot >> (32u - sh))) atomicOr(w + 1, ballot >> (32u - sh));
+        const unsigned ballot_lo = __ballot_sync(0xFFFFFFFFu, live_lo && (bits & 1u));
+        const unsigned ballot_hi = __ballot_sync(0xFFFFFFFFu, live_hi && (bits & 2u));
+        const unsigned c0 = (unsigned)(it.ty * g.tiles_x + (t & ~31));          // first block of the low half
+        if (lane == 0) {
+            uint32_t* frame_bits = ex.raw_bits + (long long)it.frame * g.words;
+            if (warp_live_lo && ballot_lo) {
+                const unsigned sh = c0 & 31u;
+                atomicOr(frame_bits + (c0 >> 5), ballot_lo << sh);
+                if (sh && (ballot_lo >> (32u - sh))) atomicOr(frame_bits + (c0 >> 5) + 1, ballot_lo >> (32u - sh));
             }
-            if (ex.pos_counts && lane < L) {
-                // lane i sees the bits of blocks c0+i, c0+i+L, ...: payload position (c0 + i) mod L
-                const int n = __popc(ballot & (ex.every << lane));
-                if (n) atomicAdd(&cta_counts[stage][(c0 + lane) & (unsigned)(L - 1)], n);
+            if (warp_live_hi && ballot_hi) {
+                const unsigned c1 = c0 + kStripThreads, sh = c1 & 31u;
+                atomicOr(frame_bits + (c1 >> 5), ballot_hi << sh);
+                if (sh && (ballot_hi >> (32u - sh))) atomicOr(frame_bits + (c1 >> 5) + 1, ballot_hi >> (32u - sh));
             }
+        }
+        if (ex.pos_counts && lane < L) {
+            // lane i sees the bits of blocks c0+i, c0+i+L, ... of both halves (128 is a multiple of L):
+            // payload position (c0 + i) mod L
+            const int n = __popc(ballot_lo & (ex.every << lane)) + __popc(ballot_hi & (ex.every << lane));
+            if (n) atomicAdd(&cta_counts[stage][(c0 + lane) & (unsigned)(L - 1)], n);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(done0 + 8 * stage);
@@ -232,7 +257,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
 }
 
 // ---- embed ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCtaThreads) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+__global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                       EmbedArgs em, StripGeom sg) {
     constexpr int kStages = kEmbedStages;
     static_assert(kStages >= 3, "a slot is refilled one iteration after its store was committed");
@@ -271,40 +296,57 @@ __global__ void __launch_bounds__(kCtaThreads) dwtsvd_embed_tma_kernel(const uin
     }
 
     // ===== consumer warps =====
-    const int t = threadIdx.x;                           // one pass: the launcher guarantees tiles_x <= kStripThreads
+    const int t = threadIdx.x, t_hi = t + kStripThreads;        // the launcher guarantees tiles_x <= 2 * kStripThreads
+    const bool live_lo = t < g.tiles_x, live_hi = t_hi < g.tiles_x;
+    const unsigned off_lo = (live_lo ? t : 0) * 8, off_hi = (live_hi ? t_hi : 0) * 8;             // dead lanes read tile 0
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
         const Item it = item_of(i, sg);
         const unsigned slot = ring + stage * sg.strip_bytes;
-        // the 32 watermark bits of this warp's tiles, funnel-shifted out of two words of the packed
-        // row; issued before the wait so that their latency hides behind it
+        // the watermark bits of this warp's tiles (32 per half), funnel-shifted out of the packed row;
+        // issued before the wait so that their latency hides behind it
         const int row = em.frame_row ? em.frame_row[it.frame] : 0;
         const uint32_t* wrow = em.wm + (long long)row * em.wm_words;
         const unsigned c0 = (unsigned)(it.ty * g.tiles_x + (t & ~31));
-        const int wi = (int)(c0 >> 5);
-        unsigned bits = 0u;
-        if (wi < em.wm_words) {
-            const unsigned lo = wrow[wi], hi = (wi + 1 < em.wm_words) ? wrow[wi + 1] : 0u;
-            bits = __funnelshift_r(lo, hi, c0 & 31u);
-        }
-        mbar_wait(full0 + 8 * stage, parity);
-        if (t < g.tiles_x) {
-            const unsigned mine = slot + t * 8;
-            float S[16], D[16];
-            {
-                uint2 rows[8];
+        unsigned wbits[2];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) rows[r] = lds_u2(mine + r * sg.pitch);
-                sums_from_rows(rows, S);
+        for (int hlf = 0; hlf < 2; ++hlf) {
+            const unsigned c = c0 + hlf * kStripThreads;
+            const int wi = (int)(c >> 5);
+            wbits[hlf] = 0u;
+            if (wi < em.wm_words) {
+                const unsigned lo = wrow[wi], hi = (wi + 1 < em.wm_words) ? wrow[wi + 1] : 0u;
+                wbits[hlf] = __funnelshift_r(lo, hi, c & 31u);
             }
-            embed_deltas<false>(S, (bits >> lane) & 1u, em.scale, em.inv_scale, 12582912.0f, D, nullptr);
+        }
+        const unsigned mybits = ((wbits[0] >> lane) & 1u) | (((wbits[1] >> lane) & 1u) << 1);
+        mbar_wait(full0 + 8 * stage, parity);
+        {
+            const unsigned mine_lo = slot + off_lo, mine_hi = slot + off_hi;
+            f2 D[16];
+            {
+                f2 S[16];
+                {
+                    uint2 ra[8], rb[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        ra[r] = lds_u2(mine_lo + r * sg.pitch);
+                        rb[r] = lds_u2(mine_hi + r * sg.pitch);
+                    }
+                    sums_from_rows_x2(ra, rb, S);
+                }
+                embed_deltas_x2(S, mybits, em.scale, em.inv_scale, 12582912.0f, D);
+            }
 #pragma unroll
             for (int i2 = 0; i2 < 4; ++i2) {
-                const unsigned d01 = __byte_perm(__float_as_uint(D[4 * i2 + 0]), __float_as_uint(D[4 * i2 + 1]), 0x5410);
-                const unsigned d23 = __byte_perm(__float_as_uint(D[4 * i2 + 2]), __float_as_uint(D[4 * i2 + 3]), 0x5410);
+                const unsigned a01 = __byte_perm(__float_as_uint(D[4 * i2 + 0].x), __float_as_uint(D[4 * i2 + 1].x), 0x5410);
+                const unsigned a23 = __byte_perm(__float_as_uint(D[4 * i2 + 2].x), __float_as_uint(D[4 * i2 + 3].x), 0x5410);
+                const unsigned b01 = __byte_perm(__float_as_uint(D[4 * i2 + 0].y), __float_as_uint(D[4 * i2 + 1].y), 0x5410);
+                const unsigned b23 = __byte_perm(__float_as_uint(D[4 * i2 + 2].y), __float_as_uint(D[4 * i2 + 3].y), 0x5410);
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const unsigned a = mine + (2 * i2 + rr) * sg.pitch;
-                    sts_u2(a, add_clamp_row(lds_u2(a), d01, d23));
+                    const unsigned ro = (2 * i2 + rr) * sg.pitch;
+                    sts_u2_if(live_lo, mine_lo + ro, add_clamp_row(lds_u2(mine_lo + ro), a01, a23));
+                    sts_u2_if(live_hi, mine_hi + ro, add_clamp_row(lds_u2(mine_hi + ro), b01, b23));
                 }
             }
         }
@@ -323,7 +365,7 @@ constexpr size_t kMaxRingBytes = 56 * 1024;
 bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const TileGeom& g) {
     return pl->dtype == B200WM_U8 && pl->elem_stride == 1 && pl->pitch_bytes == pl->width && (pl->width % 16) == 0 &&
            ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && (pl->frame_stride_bytes % 16) == 0 &&
-           (pl->n_frames <= 1 || pl->frame_stride_bytes >= pl->pitch_bytes * (long long)pl->height) && g.tiles_x >= 64 && g.tiles_x <= kStripThreads &&
+           (pl->n_frames <= 1 || pl->frame_stride_bytes >= pl->pitch_bytes * (long long)pl->height) && g.tiles_x >= 64 && g.tiles_x <= kMaxStripTiles &&
            g.tiles_y > 0 && (size_t)kEmbedStages * 8 * (size_t)pl->pitch_bytes <= kMaxRingBytes &&
            (long long)pl->n_frames * g.tiles_y < (1ll << 26) && (long long)pl->n_frames * g.tiles_y * g.tiles_y < (1ll << 40);
 }
