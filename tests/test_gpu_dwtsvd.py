@@ -289,23 +289,30 @@ def test_no_out_of_bounds_writes_guard_bytes():
 
 
 def test_random_geometries_both_paths_agree():
-    """Random plane sizes, pitches, batch sizes and per-frame watermark rows: the TMA path, the
-    vectorised path and the generic path (unaligned view) must give byte-identical planes and bits."""
+    """Random plane sizes, pitches, batch sizes and per-frame watermark rows: the TMA path (whole
+    strips, row-wise copies of pitched planes, column chunks of wide planes with an uneven last
+    chunk), the vectorised path and the generic path (unaligned view) must give byte-identical
+    planes and bits."""
     from b200wm import ops
     rng = np.random.RandomState(12345)
-    for case in range(12):
+    widths = [64, 320, 528, 1040, 1936, 2048, 2064, 3840, 4112, 6160]     # 258, 480, 514, 770 tiles: 2, 2, 3, 4 chunks
+    for case in range(20):
         n = int(rng.randint(1, 6))
         h = int(rng.choice([8, 24, 40, 72, 136, 270]))
-        w = int(rng.choice([64, 320, 528, 1040, 1936, 2048]))
+        w = widths[case % len(widths)]
         base = rng.randint(0, 256, (n, h, w)).astype(np.uint8)
         rows = rng.randint(0, 2, (3, max(1, h * w // 64)))
         frame_row = rng.randint(0, 3, n).astype(np.int32)
         outs = []
-        for mode in ("auto", "ldg", "unaligned"):
+        for mode in ("auto", "pitched16", "ldg", "unaligned"):
             ops.set_path(1 if mode == "ldg" else 0)
             if mode == "unaligned":
                 big = torch.zeros((n, h + 2, w + 13), dtype=torch.uint8, device=_dev())
                 t = big[:, 1:h + 1, 5:w + 5]
+                t.copy_(torch.from_numpy(base))
+            elif mode == "pitched16":       # rows 16-byte aligned but not tight: TMA path, one bulk copy per sample row
+                big = torch.full((n, h + 3, w + 48), 0x5A, dtype=torch.uint8, device=_dev())
+                t = big[:, 2:h + 2, 16:w + 16]
                 t.copy_(torch.from_numpy(base))
             else:
                 t = torch.from_numpy(base.copy()).to(_dev())
@@ -313,6 +320,10 @@ def test_random_geometries_both_paths_agree():
             ops.dwtsvd_embed_(t, packed, nb, frame_wm_row=torch.from_numpy(frame_row).to(_dev()))
             raw, counts = ops.dwtsvd_extract(t, payload_len=8)
             outs.append((t.cpu().numpy(), raw.cpu().numpy(), counts.cpu().numpy()))
+            if mode == "pitched16":         # nothing outside the view was written
+                big_h = big.cpu().numpy()
+                big_h[:, 2:h + 2, 16:w + 16] = 0x5A
+                assert (big_h == 0x5A).all(), (case, n, h, w)
         for other in outs[1:]:
             for a, b in zip(outs[0], other):
                 assert np.array_equal(a, b), (case, n, h, w)

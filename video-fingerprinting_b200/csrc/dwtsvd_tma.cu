@@ -3,12 +3,15 @@
 // Same arithmetic and outputs as dwtsvd.cu (the per-tile functions are shared through
 // dwtsvd_tile.cuh); what changes is how the frame strips travel:
 //
-//   * A work item is one STRIP: the 8 sample rows of one tile row of one frame.  With tight rows
-//     (pitch == width) a strip is 8*width contiguous bytes (15 KB at 1080p, 30 KB at 4K), so it
-//     moves with ONE bulk-copy TMA instruction (cp.async.bulk, SASS UBLKCP) instead of one
-//     vector load per thread and row.  (A first version used 2-D tensor-map boxes of 256x8
-//     bytes per warp; ncu showed the copy engine saturating on those small boxes at 2.3 TB/s -
-//     profiles/r01_summary.md - which is why the strips are now whole rows.)
+//   * A work item is one STRIP: the 8 sample rows of (a column chunk of) one tile row of one frame.
+//     With tight rows (pitch == width) and at most 256 tiles per row a strip is 8*width contiguous
+//     bytes (15 KB at 1080p), so it moves with ONE bulk-copy TMA instruction (cp.async.bulk, SASS
+//     UBLKCP) instead of one vector load per thread and row.  Wider planes (4K: 480 tiles per row)
+//     are cut into column chunks of at most 256 tiles and pitched planes keep their row gaps out
+//     of shared memory: both move with one bulk copy per sample row (1920 bytes at 4K), issued by
+//     eight lanes of the producer warp.  (A first version used 2-D tensor-map boxes of 256x8 bytes
+//     per warp; ncu showed the copy engine saturating on those small boxes at 2.3 TB/s -
+//     profiles/r01_summary.md - which is why the copies are now whole rows or whole strips.)
 //   * Each CTA is persistent and owns a ring of kStages strip buffers in shared memory.  It is warp
 //     specialised: eight consumer warps do the arithmetic, a ninth PRODUCER warp only moves data.
 //     The producer issues the bulk loads for the strips the CTA will need next and arms a "full"
@@ -29,9 +32,8 @@
 //     extract kernel ORs each warp's ballot into (at most two) words of a zeroed raw-bit array
 //     and the embed kernel funnel-shifts its 32 watermark bits out of two words.
 //
-// Requirements (otherwise the launcher uses the vectorised-load kernels): planar uint8 with
-// tight rows (pitch == width), width a multiple of 16 between 512 and 2048 (two tiles per thread,
-// three strips per CTA and four CTAs per SM), base and frame stride multiples of 16 bytes.
+// Requirements (otherwise the launcher uses the vectorised-load kernels): planar uint8, at least 64
+// and an even number of tiles per row, base, pitch and frame stride multiples of 16 bytes.
 #include "common.cuh"
 #include "svd4.cuh"
 #include "dwtsvd_tile.cuh"
@@ -116,29 +118,47 @@ __device__ __forceinline__ void sts_u2_if(bool pred, unsigned addr, uint2 v) {
 }
 
 // ---- work items ---------------------------------------------------------------------------------------
-// Strips are numbered i = frame * tiles_y + ty; CTA b processes i = b, b + grid, b + 2*grid, ...
+// Items are numbered i = (frame * tiles_y + ty) * chunks_x + cx; CTA b processes i = b, b + grid, ...
 struct StripGeom {
     TileGeom g;
-    int total;                       // n_frames * tiles_y  (< 2^26 so that the magic division is exact)
-    unsigned long long ty_magic;     // i / tiles_y == (i * magic) >> 40
-    unsigned pitch;                  // == width
-    unsigned strip_bytes;            // 8 * pitch
+    int total;                       // n_frames * tiles_y * chunks_x (< 2^26 so that the magic divisions are exact)
+    int chunks_x;                    // column chunks per tile row (1 up to 256 tiles per row)
+    int chunk_tiles;                 // tiles per chunk, even; the last chunk of a row may hold fewer
+    int frame_items;                 // tiles_y * chunks_x
+    unsigned long long frame_magic;  // i / frame_items == (i * magic) >> 40
+    unsigned long long chunk_magic;  // j / chunks_x    == (j * magic) >> 40
+    unsigned pitch;                  // row pitch of the plane in global memory
+    unsigned slot_pitch;             // row pitch of a strip in shared memory = 8 * chunk_tiles
+    unsigned slot_bytes;             // 8 * slot_pitch
+    int whole;                       // 1: the strip is contiguous in global memory too -> one bulk copy
     long long frame_stride;
 };
 
 struct Item {
-    int frame, ty;
+    int frame, ty, cx, tiles;        // tiles = tiles of this chunk
 };
 
+// kWhole: one chunk per tile row and tight rows (the 1080p case) - a strip is contiguous in global
+// memory, moves with a single bulk copy, and the item index needs one division only.
+template <bool kWhole>
 __device__ __forceinline__ Item item_of(int i, const StripGeom& sg) {
     Item it;
-    it.frame = (int)(((unsigned long long)(unsigned)i * sg.ty_magic) >> 40);
-    it.ty = i - it.frame * sg.g.tiles_y;
+    it.frame = (int)(((unsigned long long)(unsigned)i * sg.frame_magic) >> 40);
+    const int j = i - it.frame * sg.frame_items;
+    if (kWhole) {
+        it.ty = j;
+        it.cx = 0;
+        it.tiles = sg.g.tiles_x;
+    } else {
+        it.ty = (int)(((unsigned long long)(unsigned)j * sg.chunk_magic) >> 40);
+        it.cx = j - it.ty * sg.chunks_x;
+        it.tiles = min(sg.chunk_tiles, sg.g.tiles_x - it.cx * sg.chunk_tiles);
+    }
     return it;
 }
 
-__device__ __forceinline__ long long strip_offset(const Item& it, const StripGeom& sg) {
-    return it.frame * sg.frame_stride + (long long)it.ty * sg.strip_bytes;
+__device__ __forceinline__ long long item_offset(const Item& it, const StripGeom& sg) {
+    return it.frame * sg.frame_stride + (long long)(it.ty * 8) * sg.pitch + (long long)it.cx * sg.slot_pitch;
 }
 
 // full[s]: armed by the producer with the byte count of a load into slot s, completed by the copy engine.
@@ -156,13 +176,40 @@ __device__ __forceinline__ void init_ring(unsigned full0, unsigned done0) {
     __syncthreads();
 }
 
-__device__ __forceinline__ void load_strip(const uint8_t* src, int i, unsigned slot, unsigned bar, const StripGeom& sg) {
-    mbar_arrive_expect_tx(bar, sg.strip_bytes);
-    bulk_load(slot, src + strip_offset(item_of(i, sg), sg), sg.strip_bytes, bar);
+// Called by the whole (converged) producer warp: lane 0 arms the barrier, then it moves the whole
+// strip (kWhole) or eight lanes move one sample row each.
+template <bool kWhole>
+__device__ __forceinline__ void load_item(const uint8_t* src, int i, unsigned slot, unsigned bar, const StripGeom& sg, int lane) {
+    if (kWhole) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar, sg.slot_bytes);
+            bulk_load(slot, src + item_offset(item_of<true>(i, sg), sg), sg.slot_bytes, bar);
+        }
+        return;
+    }
+    const Item it = item_of<false>(i, sg);
+    const unsigned row_bytes = (unsigned)it.tiles * 8u;
+    if (lane == 0) mbar_arrive_expect_tx(bar, 8u * row_bytes);
+    __syncwarp();
+    if (lane < 8)
+        bulk_load(slot + lane * sg.slot_pitch, src + item_offset(it, sg) + (unsigned long long)lane * sg.pitch, row_bytes, bar);
+}
+
+template <bool kWhole>
+__device__ __forceinline__ void store_item(uint8_t* dst, int i, unsigned slot, const StripGeom& sg, int lane) {
+    if (kWhole) {
+        if (lane == 0) bulk_store(dst + item_offset(item_of<true>(i, sg), sg), slot, sg.slot_bytes);
+    } else {
+        const Item it = item_of<false>(i, sg);
+        if (lane < 8)
+            bulk_store(dst + item_offset(it, sg) + (unsigned long long)lane * sg.pitch, slot + lane * sg.slot_pitch, (unsigned)it.tiles * 8u);
+    }
+    bulk_commit();
 }
 
 // ---- extract -------------------------------------------------------------------------------------------
 // raw_bits must be zero on entry (the launcher clears it): warps OR their bits in.
+template <bool kWhole>
 __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src,
                                                                                                ExtractArgs ex, StripGeom sg) {
     constexpr int kStages = kExtractStages;
@@ -182,37 +229,35 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
 
     if (warp == kConsumerWarps) {
         // ===== producer warp: loads, and the per-strip flush of the vote counters =====
-        if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < kStages; ++s)
-                if ((int)blockIdx.x + s * step < sg.total)
-                    load_strip(src, (int)blockIdx.x + s * step, ring + s * sg.strip_bytes, full0 + 8 * s, sg);
-        }
+        for (int s = 0; s < kStages; ++s)
+            if ((int)blockIdx.x + s * step < sg.total)
+                load_item<kWhole>(src, (int)blockIdx.x + s * step, ring + s * sg.slot_bytes, full0 + 8 * s, sg, lane);
         for (int i = (int)blockIdx.x; i < sg.total; i += step) {
             mbar_wait(done0 + 8 * stage, parity);        // every consumer warp is done with this slot
             if (ex.pos_counts && lane < L) {
                 const int n = cta_counts[stage][lane];
                 if (n) {
-                    atomicAdd(&ex.pos_counts[(long long)item_of(i, sg).frame * L + lane], n);
+                    atomicAdd(&ex.pos_counts[(long long)item_of<kWhole>(i, sg).frame * L + lane], n);
                     cta_counts[stage][lane] = 0;
                 }
             }
             __syncwarp();
-            if (lane == 0 && i + kStages * step < sg.total)
-                load_strip(src, i + kStages * step, ring + stage * sg.strip_bytes, full0 + 8 * stage, sg);
+            if (i + kStages * step < sg.total)
+                load_item<kWhole>(src, i + kStages * step, ring + stage * sg.slot_bytes, full0 + 8 * stage, sg, lane);
             if (++stage == kStages) { stage = 0; parity ^= 1u; }
         }
         return;
     }
 
     // ===== consumer warps =====
-    const int t = threadIdx.x, t_hi = t + kStripThreads;        // the launcher guarantees tiles_x <= 2 * kStripThreads
-    const bool live_lo = t < g.tiles_x, live_hi = t_hi < g.tiles_x;
-    const bool warp_live_lo = (t & ~31) < g.tiles_x, warp_live_hi = (t_hi & ~31) < g.tiles_x;     // warp-uniform
-    const unsigned off_lo = (live_lo ? t : 0) * 8, off_hi = (live_hi ? t_hi : 0) * 8;             // dead lanes read tile 0
+    const int t = threadIdx.x, t_hi = t + kStripThreads;        // the launcher guarantees chunk_tiles <= 2 * kStripThreads
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
-        const Item it = item_of(i, sg);
-        const unsigned slot = ring + stage * sg.strip_bytes;
+        const Item it = item_of<kWhole>(i, sg);
+        const unsigned slot = ring + stage * sg.slot_bytes;
+        const bool live_lo = t < it.tiles, live_hi = t_hi < it.tiles;
+        const bool warp_live_lo = (t & ~31) < it.tiles, warp_live_hi = (t_hi & ~31) < it.tiles;     // warp-uniform
+        const unsigned off_lo = (live_lo ? t : 0) * 8, off_hi = (live_hi ? t_hi : 0) * 8;           // dead lanes read tile 0
         mbar_wait(full0 + 8 * stage, parity);
         unsigned bits;
         {
@@ -221,8 +266,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
                 uint2 ra[8], rb[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    ra[r] = lds_u2(slot + r * sg.pitch + off_lo);
-                    rb[r] = lds_u2(slot + r * sg.pitch + off_hi);
+                    ra[r] = lds_u2(slot + r * sg.slot_pitch + off_lo);
+                    rb[r] = lds_u2(slot + r * sg.slot_pitch + off_hi);
                 }
                 sums_from_rows_x2(ra, rb, S);
             }
@@ -230,7 +275,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
         }
         const unsigned ballot_lo = __ballot_sync(0xFFFFFFFFu, live_lo && (bits & 1u));
         const unsigned ballot_hi = __ballot_sync(0xFFFFFFFFu, live_hi && (bits & 2u));
-        const unsigned c0 = (unsigned)(it.ty * g.tiles_x + (t & ~31));          // first block of the low half
+        const unsigned c0 = (unsigned)(it.ty * g.tiles_x + it.cx * sg.chunk_tiles + (t & ~31));     // first block of the low half
         if (lane == 0) {
             uint32_t* frame_bits = ex.raw_bits + (long long)it.frame * g.words;
             if (warp_live_lo && ballot_lo) {
@@ -257,6 +302,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
 }
 
 // ---- embed ----------------------------------------------------------------------------------------------
+template <bool kWhole>
 __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                       EmbedArgs em, StripGeom sg) {
     constexpr int kStages = kEmbedStages;
@@ -273,21 +319,21 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
     unsigned parity = 0;
 
     if (warp == kConsumerWarps) {
-        // ===== producer warp (one lane): loads, stores, refills =====
-        if (lane != 0) return;
+        // ===== producer warp: loads, stores, refills (a single lane when a strip is one copy) =====
+        if (kWhole && lane != 0) return;
 #pragma unroll
         for (int s = 0; s < kStages - 1; ++s)            // the last slot is filled by the first refill
             if ((int)blockIdx.x + s * step < sg.total)
-                load_strip(src, (int)blockIdx.x + s * step, ring + s * sg.strip_bytes, full0 + 8 * s, sg);
+                load_item<kWhole>(src, (int)blockIdx.x + s * step, ring + s * sg.slot_bytes, full0 + 8 * s, sg, lane);
         int refill = kStages - 1;
         for (int i = (int)blockIdx.x; i < sg.total; i += step) {
             mbar_wait(done0 + 8 * stage, parity);        // every consumer warp has rewritten its tiles of this strip
-            bulk_store(dst + strip_offset(item_of(i, sg), sg), ring + stage * sg.strip_bytes, sg.strip_bytes);
-            bulk_commit();
-            // the slot stored one iteration ago has been read by now (at most this store pending)
+            store_item<kWhole>(dst, i, ring + stage * sg.slot_bytes, sg, lane);
+            // the slot stored one iteration ago has been read by now (every lane: at most its newest store pending)
             bulk_wait_read<1>();
+            if (!kWhole) __syncwarp();
             const int nxt = i + (kStages - 1) * step;    // the strip kStages-1 iterations ahead
-            if (nxt < sg.total) load_strip(src, nxt, ring + refill * sg.strip_bytes, full0 + 8 * refill, sg);
+            if (nxt < sg.total) load_item<kWhole>(src, nxt, ring + refill * sg.slot_bytes, full0 + 8 * refill, sg, lane);
             refill = stage;
             if (++stage == kStages) { stage = 0; parity ^= 1u; }
         }
@@ -296,17 +342,17 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
     }
 
     // ===== consumer warps =====
-    const int t = threadIdx.x, t_hi = t + kStripThreads;        // the launcher guarantees tiles_x <= 2 * kStripThreads
-    const bool live_lo = t < g.tiles_x, live_hi = t_hi < g.tiles_x;
-    const unsigned off_lo = (live_lo ? t : 0) * 8, off_hi = (live_hi ? t_hi : 0) * 8;             // dead lanes read tile 0
+    const int t = threadIdx.x, t_hi = t + kStripThreads;        // the launcher guarantees chunk_tiles <= 2 * kStripThreads
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
-        const Item it = item_of(i, sg);
-        const unsigned slot = ring + stage * sg.strip_bytes;
+        const Item it = item_of<kWhole>(i, sg);
+        const unsigned slot = ring + stage * sg.slot_bytes;
+        const bool live_lo = t < it.tiles, live_hi = t_hi < it.tiles;
+        const unsigned off_lo = (live_lo ? t : 0) * 8, off_hi = (live_hi ? t_hi : 0) * 8;           // dead lanes read tile 0
         // the watermark bits of this warp's tiles (32 per half), funnel-shifted out of the packed row;
         // issued before the wait so that their latency hides behind it
         const int row = em.frame_row ? em.frame_row[it.frame] : 0;
         const uint32_t* wrow = em.wm + (long long)row * em.wm_words;
-        const unsigned c0 = (unsigned)(it.ty * g.tiles_x + (t & ~31));
+        const unsigned c0 = (unsigned)(it.ty * g.tiles_x + it.cx * sg.chunk_tiles + (t & ~31));
         unsigned wbits[2];
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
@@ -329,8 +375,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
                     uint2 ra[8], rb[8];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        ra[r] = lds_u2(mine_lo + r * sg.pitch);
-                        rb[r] = lds_u2(mine_hi + r * sg.pitch);
+                        ra[r] = lds_u2(mine_lo + r * sg.slot_pitch);
+                        rb[r] = lds_u2(mine_hi + r * sg.slot_pitch);
                     }
                     sums_from_rows_x2(ra, rb, S);
                 }
@@ -344,7 +390,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
                 const unsigned b23 = __byte_perm(__float_as_uint(D[4 * i2 + 2].y), __float_as_uint(D[4 * i2 + 3].y), 0x5410);
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const unsigned ro = (2 * i2 + rr) * sg.pitch;
+                    const unsigned ro = (2 * i2 + rr) * sg.slot_pitch;
                     sts_u2_if(live_lo, mine_lo + ro, add_clamp_row(lds_u2(mine_lo + ro), a01, a23));
                     sts_u2_if(live_hi, mine_hi + ro, add_clamp_row(lds_u2(mine_hi + ro), b01, b23));
                 }
@@ -358,16 +404,24 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-// three 15 KB strips (1080p) leave room for four CTAs per SM; wider planes would starve the SM of
-// warps (two CTAs at 4K), where the vectorised-load kernels measured faster (profiles/r01_summary.md)
-constexpr size_t kMaxRingBytes = 56 * 1024;
+// three strips of at most 2 KB x 8 rows leave room for four (extract) / three (embed) CTAs per SM
+static int strip_chunks(const TileGeom& g, int* chunk_tiles) {
+    const int chunks = (g.tiles_x + kMaxStripTiles - 1) / kMaxStripTiles;
+    int per = (g.tiles_x + chunks - 1) / chunks;
+    per += per & 1;                                   // even: 16-byte aligned chunk starts
+    *chunk_tiles = per;
+    return (g.tiles_x + per - 1) / per;
+}
 
 bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const TileGeom& g) {
-    return pl->dtype == B200WM_U8 && pl->elem_stride == 1 && pl->pitch_bytes == pl->width && (pl->width % 16) == 0 &&
-           ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && (pl->frame_stride_bytes % 16) == 0 &&
-           (pl->n_frames <= 1 || pl->frame_stride_bytes >= pl->pitch_bytes * (long long)pl->height) && g.tiles_x >= 64 && g.tiles_x <= kMaxStripTiles &&
-           g.tiles_y > 0 && (size_t)kEmbedStages * 8 * (size_t)pl->pitch_bytes <= kMaxRingBytes &&
-           (long long)pl->n_frames * g.tiles_y < (1ll << 26) && (long long)pl->n_frames * g.tiles_y * g.tiles_y < (1ll << 40);
+    if (!(pl->dtype == B200WM_U8 && pl->elem_stride == 1 && (pl->pitch_bytes % 16) == 0 && ((uintptr_t)a % 16) == 0 &&
+          ((uintptr_t)b % 16) == 0 && (pl->frame_stride_bytes % 16) == 0 && g.tiles_x >= 64 && (g.tiles_x % 2) == 0 && g.tiles_y > 0))
+        return false;
+    if (pl->n_frames > 1 && pl->frame_stride_bytes < pl->pitch_bytes * (long long)pl->height) return false;
+    int chunk_tiles = 0;
+    const long long frame_items = (long long)g.tiles_y * strip_chunks(g, &chunk_tiles);
+    const long long items = pl->n_frames * frame_items;
+    return items < (1ll << 26) && items * frame_items < (1ll << 40);     // exact magic divisions
 }
 
 template <typename Kernel>
@@ -389,36 +443,44 @@ static int persistent_grid(Kernel kernel, size_t smem, int* blocks) {
 static StripGeom make_strip_geom(const TileGeom& g, const b200wm_plane* pl) {
     StripGeom sg;
     sg.g = g;
-    sg.total = pl->n_frames * g.tiles_y;
-    sg.ty_magic = (1ull << 40) / (unsigned long long)g.tiles_y + 1ull;
+    sg.chunks_x = strip_chunks(g, &sg.chunk_tiles);
+    sg.frame_items = g.tiles_y * sg.chunks_x;
+    sg.total = pl->n_frames * sg.frame_items;
+    sg.frame_magic = (1ull << 40) / (unsigned long long)sg.frame_items + 1ull;
+    sg.chunk_magic = (1ull << 40) / (unsigned long long)sg.chunks_x + 1ull;
     sg.pitch = (unsigned)pl->pitch_bytes;
-    sg.strip_bytes = 8u * sg.pitch;
+    sg.slot_pitch = 8u * (unsigned)sg.chunk_tiles;
+    sg.slot_bytes = 8u * sg.slot_pitch;
+    sg.whole = (sg.chunks_x == 1 && sg.slot_pitch == sg.pitch) ? 1 : 0;
     sg.frame_stride = pl->frame_stride_bytes;
     return sg;
 }
 
 int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const TileGeom& g, ExtractArgs xa, cudaStream_t stream) {
-    const size_t smem = (size_t)kExtractStages * 8 * (size_t)pl->pitch_bytes;
+    const StripGeom sg = make_strip_geom(g, pl);
+    const size_t smem = (size_t)kExtractStages * sg.slot_bytes;
     int blocks = 0;
-    int rc = persistent_grid(dwtsvd_extract_tma_kernel, smem, &blocks);
+    int rc = sg.whole ? persistent_grid(dwtsvd_extract_tma_kernel<true>, smem, &blocks)
+                      : persistent_grid(dwtsvd_extract_tma_kernel<false>, smem, &blocks);
     if (rc) return rc;
-    const long long strips = (long long)pl->n_frames * g.tiles_y;
-    if (strips < blocks) blocks = (int)strips;
-    dwtsvd_extract_tma_kernel<<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, xa, make_strip_geom(g, pl));
+    if (sg.total < blocks) blocks = sg.total;
+    if (sg.whole) dwtsvd_extract_tma_kernel<true><<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, xa, sg);
+    else dwtsvd_extract_tma_kernel<false><<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, xa, sg);
     B200WM_LAUNCH_CHECK("dwtsvd_extract_tma_kernel");
     return B200WM_OK;
 }
 
 int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, const TileGeom& g, EmbedArgs ea,
                             cudaStream_t stream) {
-    const size_t smem = (size_t)kEmbedStages * 8 * (size_t)pl->pitch_bytes;
+    const StripGeom sg = make_strip_geom(g, pl);
+    const size_t smem = (size_t)kEmbedStages * sg.slot_bytes;
     int blocks = 0;
-    int rc = persistent_grid(dwtsvd_embed_tma_kernel, smem, &blocks);
+    int rc = sg.whole ? persistent_grid(dwtsvd_embed_tma_kernel<true>, smem, &blocks)
+                      : persistent_grid(dwtsvd_embed_tma_kernel<false>, smem, &blocks);
     if (rc) return rc;
-    const long long strips = (long long)pl->n_frames * g.tiles_y;
-    if (strips < blocks) blocks = (int)strips;
-    dwtsvd_embed_tma_kernel<<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea,
-                                                                     make_strip_geom(g, pl));
+    if (sg.total < blocks) blocks = sg.total;
+    if (sg.whole) dwtsvd_embed_tma_kernel<true><<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea, sg);
+    else dwtsvd_embed_tma_kernel<false><<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea, sg);
     B200WM_LAUNCH_CHECK("dwtsvd_embed_tma_kernel");
     return B200WM_OK;
 }
