@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libb200wm.so")
 SOURCES = ["api.cu", "dwtsvd.cu", "dwtsvd_tma.cu", "dwtsvd_copies.cu", "dct8.cu", "vote.cu", "bracket.cu", "fused_rgb.cu", "attacks.cu", "pipeline.cu"]
-HEADERS = ["common.cuh", "svd4.cuh", "dwtsvd_tile.cuh", "dct8.cuh", os.path.join("..", "..", "include", "b200wm.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "b200wm.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

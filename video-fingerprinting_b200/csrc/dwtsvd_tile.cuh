@@ -203,25 +203,28 @@ __device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, fl
 // ------------------------------------------------------------------------------------------
 // two tiles per thread, packed FP32 (svd4x2.cuh); lane .x = first tile, lane .y = second tile
 // ------------------------------------------------------------------------------------------
+// The four bytes of a 2x2 are first gathered into one register (PRMT, integer pipe) and then summed
+// into the magic float pattern by ONE dp4a: IDP issues at half rate on the FMA-heavy pipe, which is the
+// co-critical resource of these kernels next to the issue slots (profiles/r01_summary.md).
 __device__ __forceinline__ void sums_from_rows_x2(const uint2 (&ra)[8], const uint2 (&rb)[8], f2 (&S)[16]) {
-    constexpr unsigned kMagic = 0x4B000000u;
+    constexpr unsigned kMagic = 0x4B000000u, kOnes = 0x01010101u;
     const f2 minus_magic = bc2(-8388608.0f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         unsigned sa[4], sb[4];
         {
             const uint2 a = ra[2 * i], b = ra[2 * i + 1];
-            sa[0] = __dp4a(b.x, 0x00000101u, __dp4a(a.x, 0x00000101u, kMagic));
-            sa[1] = __dp4a(b.x, 0x01010000u, __dp4a(a.x, 0x01010000u, kMagic));
-            sa[2] = __dp4a(b.y, 0x00000101u, __dp4a(a.y, 0x00000101u, kMagic));
-            sa[3] = __dp4a(b.y, 0x01010000u, __dp4a(a.y, 0x01010000u, kMagic));
+            sa[0] = __dp4a(__byte_perm(a.x, b.x, 0x5410), kOnes, kMagic);
+            sa[1] = __dp4a(__byte_perm(a.x, b.x, 0x7632), kOnes, kMagic);
+            sa[2] = __dp4a(__byte_perm(a.y, b.y, 0x5410), kOnes, kMagic);
+            sa[3] = __dp4a(__byte_perm(a.y, b.y, 0x7632), kOnes, kMagic);
         }
         {
             const uint2 a = rb[2 * i], b = rb[2 * i + 1];
-            sb[0] = __dp4a(b.x, 0x00000101u, __dp4a(a.x, 0x00000101u, kMagic));
-            sb[1] = __dp4a(b.x, 0x01010000u, __dp4a(a.x, 0x01010000u, kMagic));
-            sb[2] = __dp4a(b.y, 0x00000101u, __dp4a(a.y, 0x00000101u, kMagic));
-            sb[3] = __dp4a(b.y, 0x01010000u, __dp4a(a.y, 0x01010000u, kMagic));
+            sb[0] = __dp4a(__byte_perm(a.x, b.x, 0x5410), kOnes, kMagic);
+            sb[1] = __dp4a(__byte_perm(a.x, b.x, 0x7632), kOnes, kMagic);
+            sb[2] = __dp4a(__byte_perm(a.y, b.y, 0x5410), kOnes, kMagic);
+            sb[3] = __dp4a(__byte_perm(a.y, b.y, 0x7632), kOnes, kMagic);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)

@@ -106,11 +106,11 @@ __device__ __forceinline__ Pair2 top_singular_x2(const f2 (&S)[16], f2 (&v)[4]) 
     Pair2 out;
     out.zero_x = !(tr_raw.x > 0.0f);
     out.zero_y = !(tr_raw.y > 0.0f);
-    const unsigned ex = __float_as_uint(tr_raw.x) & 0x7F800000u, ey = __float_as_uint(tr_raw.y) & 0x7F800000u;
-    const f2 down = make_float2(__uint_as_float(0x7E800000u - ex), __uint_as_float(0x7E800000u - ey));
-#pragma unroll
-    for (int k = 0; k < 10; ++k) G[k] = mul2(G[k], down);
-    const f2 tr = mul2(tr_raw, down);
+    // The scalar routine first scales G by an exact power of two so that tr(G) lies in [0.5, 1).  That
+    // scaling commutes with every operation below (powers of two, no rounding) and only exists to keep
+    // arbitrary float input in range; the packed routine is used on uint8 planes only, where S <= 1020,
+    // |G| < 2^23 and the largest intermediate (x.w) stays below 2^123, so it is skipped - same bits out.
+    const f2 tr = tr_raw;
 
     f2 x[4], w[4];
     w[0] = add2(add2(G[0], G[1]), add2(G[2], G[3]));
@@ -132,8 +132,7 @@ __device__ __forceinline__ Pair2 top_singular_x2(const f2 (&S)[16], f2 (&v)[4]) 
     const bool done_x = ((gap.x > 0.0f) && (rr.x <= thr.x)) || out.zero_x;
     const bool done_y = ((gap.y > 0.0f) && (rr.y <= thr.y)) || out.zero_y;
 
-    const f2 up = make_float2(__uint_as_float(ex + 0x00800000u), __uint_as_float(ey + 0x00800000u));
-    const f2 lam_full = mul2(div_pos2(xw, xx), up);
+    const f2 lam_full = div_pos2(xw, xx);
     const f2 root = sqrt_pos2(lam_full);
     out.sigma0 = make_float2(out.zero_x ? 0.0f : root.x, out.zero_y ? 0.0f : root.y);
     if (kWantVec) {
