@@ -51,7 +51,7 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--frames", type=int, default=3000, help="frames per GPU")
     p.add_argument("--e2e-frames", type=int, default=3000)
-    p.add_argument("--cpu-frames-per-core", type=int, default=1)
+    p.add_argument("--cpu-frames-per-core", type=int, default=8)     # ~2 s per frame and core: 10-20 s of CPU work
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--path", type=int, default=0, choices=[0, 1],
@@ -423,25 +423,56 @@ def main():
         dist.destroy_process_group()
 
 
+def gpu_cpu_affinity(index):
+    """CPUs on the NUMA node of GPU ``index`` (NVML), or None.  Pinned staging buffers are placed on the
+    node of the thread that allocates them; from the far socket the PCIe copies of the end-to-end path
+    measured a third slower, so the bench binds itself next to its GPU while it allocates and streams."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
 def run_e2e(args, ops, deg, src, wm_packed, wm_len, frame_row, block_num, words, dev, payloads, world=1):
+    before = os.sched_getaffinity(0)
+    near = gpu_cpu_affinity(dev.index or 0)
+    if near:
+        os.sched_setaffinity(0, near)
+    try:
+        res = _run_e2e(args, ops, deg, src, wm_packed, wm_len, frame_row, block_num, words, dev, payloads, world)
+    finally:
+        os.sched_setaffinity(0, before)
+    res["host_affinity"] = f"{len(near)} CPUs of the GPU's NUMA node" if near else "unbound"
+    return res
+
+
+def _run_e2e(args, ops, deg, src, wm_packed, wm_len, frame_row, block_num, words, dev, payloads, world=1):
     """Same metric through the C ABI's HOST-buffer entry points: pinned host Y planes ->
     b200wm_dwtsvd_mark_host (H2D, embed, D2H of the marked planes) -> b200wm_dwtsvd_detect_host on the
     marked host planes (H2D, extract, per-frame vote, D2H of the patterns).  Copies, kernels and
-    downloads of successive 125-frame chunks overlap on two streams inside the library."""
+    downloads of successive 32-frame chunks overlap on three streams inside the library."""
     import torch.distributed as dist
     n = min(args.e2e_frames, src.shape[0])
     host_in = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
     host_marked = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
     host_in.copy_(src[:n])
     torch.cuda.synchronize()
-    rows_host = ops.unpack_bits(wm_packed, wm_len)                   # [segments, block_num] 0/1 on the host
+    rows_host = wm_packed.cpu().contiguous()                         # packed payload rows [segments, words] on the host
     frame_row_host = frame_row[:n].cpu()
     perm = deg.payload_idx
-    chunk = 125
+    chunk = 0
     patterns = None
 
     def one_pass():
-        ops.dwtsvd_mark_host(host_in, host_marked, rows_host, scale=15.0, frame_wm_row=frame_row_host, chunk_frames=chunk)
+        ops.dwtsvd_mark_host(host_in, host_marked, rows_host, scale=15.0, frame_wm_row=frame_row_host, chunk_frames=chunk,
+                             wm_len=wm_len)
         return ops.dwtsvd_detect_host(host_marked, perm, scale=15.0, chunk_frames=chunk)
 
     one_pass()
@@ -457,10 +488,30 @@ def run_e2e(args, ops, deg, src, wm_packed, wm_len, frame_row, block_num, words,
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     ok = float((patterns == payloads[np.arange(n) // SEGMENT_FRAMES]).all(axis=1).mean())
+    # what the link itself delivers on this box (plain pinned copies of 1 GB, one direction at a time and both
+    # together), so that the end-to-end figure can be read against its own ceiling
+    m = min(n, 500)
+    scratch = torch.empty((m, H, W), dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(device=dev)
+
+    def timed_copy(up, down):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if up:
+            scratch.copy_(host_in[:m], non_blocking=True)
+        if down:
+            with torch.cuda.stream(side):
+                host_marked[:m].copy_(src[:m], non_blocking=True)
+        torch.cuda.synchronize()
+        return m * H * W / (time.perf_counter() - t0) / 1e9
+    timed_copy(True, True)
+    link = {"h2d_GBs": round(timed_copy(True, False), 1), "d2h_GBs": round(timed_copy(False, True), 1),
+            "each_way_GBs_when_both": round(timed_copy(True, True), 1)}
     return {"value": n * world * steps / dt, "unit": "frames/s", "h2d_bytes_per_step": 2 * n * H * W,
             "d2h_bytes_per_step": n * H * W + n * PAYLOAD_LEN, "frames_per_gpu": n, "steps": steps,
+            "h2d_GBs_per_gpu": 2 * n * H * W * steps / dt / 1e9, "link_probe": link,
             "path": "b200wm_dwtsvd_mark_host + b200wm_dwtsvd_detect_host on pinned host Y planes (H2D, embed, D2H marked; "
-                    "H2D marked, extract + vote, D2H patterns), 125-frame chunks on 2 streams inside the library",
+                    "H2D marked, extract + vote, D2H patterns), 32-frame chunks over 3 buffers and 3 streams inside the library",
             "frames_exact": ok}
 
 

@@ -250,7 +250,7 @@ B200WM_API int b200wm_dwtsvd_extract_rgb8(const uint8_t* src, int32_t n_frames, 
  * come from and go to ffmpeg pipes, video/frame_reader.py:53-64, video/frame_writer.py:41-44).
  * `plane` describes planar uint8 planes in host memory; every other pointer is a host pointer too.
  * The batch is streamed through the current device in chunks of `chunk_frames` (0 = automatic) on
- * two internal streams (upload, kernels and download overlap); the calls return when the results
+ * three internal streams (upload, kernels and download overlap); the calls return when the results
  * are in host memory.  Pinned host memory gives full PCIe speed.
  *
  * mark:   Embedder's per-frame encode for the whole batch (b200wm_dwtsvd_embed semantics).
@@ -263,6 +263,10 @@ B200WM_API int b200wm_dwtsvd_mark_host(const uint8_t* src_host, uint8_t* dst_hos
 B200WM_API int b200wm_dwtsvd_detect_host(const uint8_t* src_host, const b200wm_plane* plane, float scale, int32_t payload_len,
                              const int32_t* perm_host, uint8_t* patterns_host, uint32_t* raw_bits_host,
                              int32_t* pos_counts_host, int32_t chunk_frames);
+
+/* Streams and device scratch of the two calls above persist between calls (per device, grow-only); this
+ * frees them for the current device. */
+B200WM_API int b200wm_host_scratch_release(void);
 
 /* ---- distortion channel for robustness studies (no counterpart in the reference) ---- */
 /*

@@ -67,6 +67,21 @@ def main():
         report(f"4K embed+extract ({tag})", ms_e + ms_x, n, 3 * h * w)
     ops.set_path(0)
     del src, dst
+    # ---- chroma plane of yuv420p 1080p frames, marked in place through a strided view
+    h, w, n = 1080, 1920, 1024
+    frames = torch.empty((n, h * w * 3 // 2), dtype=torch.uint8, device=DEV)
+    frames[:, :h * w] = planes(n, h, w).view(n, -1)
+    frames[:, h * w:] = planes(n, h // 2, w, seed=3).view(n, -1)
+    u = ops.i420_plane(frames, h, w, "u")
+    wmu, lnu = ops.pack_bits(Shuffler(key=0).generate_wm(payload, (1, (h // 2) * (w // 2) // 64))[0], device=DEV)
+    for path, tag in ((0, "tma"), (1, "ldg")):
+        ops.set_path(path)
+        ms_e = timed(lambda: ops.dwtsvd_embed_(u, wmu, lnu))
+        ms_x = timed(lambda: ops.dwtsvd_extract(u, payload_len=8))
+        report(f"I420 U plane 960x540 embed in place ({tag})", ms_e, n, 2 * (h // 2) * (w // 2))
+        report(f"I420 U plane 960x540 extract ({tag})", ms_x, n, (h // 2) * (w // 2))
+    ops.set_path(0)
+    del frames
     # ---- fused rgb24 1080p frames (reference default flow: U channel of the converted frame)
     h, w, n = 1080, 1920, 512
     # coloured content: three different smooth fields plus noise, so chroma is not a flat 0.5

@@ -295,10 +295,10 @@ def test_random_geometries_both_paths_agree():
     planes and bits."""
     from b200wm import ops
     rng = np.random.RandomState(12345)
-    widths = [64, 320, 528, 1040, 1936, 2048, 2064, 3840, 4112, 6160]     # 258, 480, 514, 770 tiles: 2, 2, 3, 4 chunks
-    for case in range(20):
+    widths = [64, 320, 528, 784, 1024, 1040, 1936, 2048, 2064, 3840, 4112, 6160]   # <= 128 tiles: two tile rows per item; 258, 480, 514, 770 tiles: 2, 2, 3, 4 chunks
+    for case in range(24):
         n = int(rng.randint(1, 6))
-        h = int(rng.choice([8, 24, 40, 72, 136, 270]))
+        h = int(rng.choice([8, 16, 24, 40, 64, 72, 136, 270]))
         w = widths[case % len(widths)]
         base = rng.randint(0, 256, (n, h, w)).astype(np.uint8)
         rows = rng.randint(0, 2, (3, max(1, h * w // 64)))
@@ -370,3 +370,42 @@ def test_multi_copy_embed_equals_single_embeds(h, w, pad):
     if n > 32:
         with pytest.raises(IndexError):          # watermark shorter than the block count, as embed/dwt_dct_svd_encoder.py:36
             ops.dwtsvd_embed_copies(src, packed[:, :1].contiguous(), 32, 2)
+
+
+@pytest.mark.parametrize("which", ["y", "u", "v"])
+def test_i420_native_planes(which):
+    """mark / read a plane of planar yuv420p frames in place (the wire format of
+    video/frame_writer.py:34) through strided views: the chosen plane matches the oracle within 1 LSB,
+    its payload decodes, and the two other planes are not touched."""
+    from b200wm import ops
+    DEV = _dev()
+    n, h, w = 4, 1080, 1920
+    fb = h * w * 3 // 2
+    rng = np.random.RandomState(7)
+    host = np.empty((n, fb), dtype=np.uint8)
+    for f in range(n):
+        host[f, :h * w] = synth.luma_plane_u8(h, w, f, 11).reshape(-1)
+        host[f, h * w:] = np.clip(np.rint(128 + 20 * np.sin(np.arange(h * w // 2) / 977.0) + rng.normal(0, 3, h * w // 2)), 16, 240)
+    frames = torch.from_numpy(host).to(DEV)
+    plane = ops.i420_plane(frames, h, w, which)
+    ph, pw = plane.shape[1], plane.shape[2]
+    wm = o_pay.generate_wm(PAYLOAD, (1, ph * pw // 64), KEY)
+    packed, nb = ops.pack_bits(wm[0], device=DEV)
+    ops.dwtsvd_embed_(plane, packed, nb)
+    raw, counts = ops.dwtsvd_extract(plane, payload_len=8)
+    perm = torch.from_numpy(o_pay.permutation(8, KEY).astype(np.int32)).to(DEV)
+    patterns, _ = ops.vote_finish(counts, ph * pw // 64, perm)
+    assert (patterns.cpu().numpy() == PAYLOAD[None, :]).all()
+    out = frames.cpu().numpy()
+    lo = {"y": 0, "u": h * w, "v": h * w + ph * pw}[which]
+    untouched = np.ones(fb, bool)
+    untouched[lo:lo + ph * pw] = False
+    assert np.array_equal(out[:, untouched], host[:, untouched]), "another plane was written"
+    for f in (0, n - 1):
+        src_plane = host[f, lo:lo + ph * pw].reshape(ph, pw)
+        want = o_svd.embed_plane_u8(src_plane, wm[0])
+        _, edge_floor, _ = knife_edge_blocks(src_plane.astype(np.float32))
+        ok = ~tile_mask_to_pixels(edge_floor, (ph, pw))
+        got = out[f, lo:lo + ph * pw].reshape(ph, pw)
+        assert np.abs(got.astype(np.int16) - want)[ok].max() <= 1        # tolerance: 1 LSB (north_star)
+        _assert_bits_match(ops.unpack_bits(raw[f:f + 1], ph * pw // 64), o_svd.extract_plane(got), got.astype(np.float32), f"i420 {which}")

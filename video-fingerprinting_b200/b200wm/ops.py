@@ -85,6 +85,25 @@ def geometry(height, width):
             int(lib.b200wm_words_per_frame(height, width)))
 
 
+def i420_plane(frames, height, width, which="y"):
+    """Strided [N, h, w] view (no copy) of one plane of planar I420 / yuv420p frames - the wire format the
+    reference hands to its encoder (video/frame_writer.py:34, pix_fmt='yuv420p').  ``frames`` is a
+    uint8 tensor ``[N, width*height*3/2]``; ``which`` is 'y' (height x width), 'u' or 'v' (half size).
+    Every DWT/SVD entry point takes the view directly, so a mark can be written into (and read from)
+    the luma or a chroma plane of 4:2:0 video without a colour-space round trip."""
+    if frames.dim() != 2 or frames.dtype != torch.uint8 or frames.shape[1] != width * height * 3 // 2 or width % 2 or height % 2:
+        raise ValueError("frames must be uint8 [N, width*height*3/2] with even width and height")
+    n, fb = frames.shape
+    stride = frames.stride(0)
+    if which == "y":
+        return frames.as_strided((n, height, width), (stride, width, 1), frames.storage_offset())
+    ch, cw = height // 2, width // 2
+    off = width * height + (0 if which == "u" else ch * cw)
+    if which not in ("u", "v"):
+        raise ValueError("which must be 'y', 'u' or 'v'")
+    return frames.as_strided((n, ch, cw), (stride, cw, 1), frames.storage_offset() + off)
+
+
 # ----------------------------------------------------------------------------- bit packing
 def pack_bits(bits, device=None):
     """0/1 array ``[rows, n]`` or ``[n]`` -> (int32 tensor [rows, words], n).  Host-side, tiny."""
@@ -338,16 +357,23 @@ def _host_planes(t):
     return t, Plane(_lib.U8, n, h, w, t.stride(1), t.stride(0) if n > 1 else 0, 1, 0)
 
 
-def dwtsvd_mark_host(src, dst, wm_rows, scale=15.0, frame_wm_row=None, chunk_frames=0):
+def dwtsvd_mark_host(src, dst, wm_rows, scale=15.0, frame_wm_row=None, chunk_frames=0, wm_len=None):
     """Mark host-resident planes: ``src``/``dst`` CPU uint8 ``[N, H, W]`` (pinned for full PCIe speed; may be
-    the same array), ``wm_rows`` 0/1 array ``[rows, n]``.  One C-ABI call; copies and kernels overlap inside."""
+    the same array), ``wm_rows`` 0/1 array ``[rows, n]`` - or, with ``wm_len`` given, rows already packed by
+    ``pack_bits`` (CPU int32 ``[rows, words]``).  One C-ABI call; copies and kernels overlap inside."""
     require_cuda()
     s, pl = _host_planes(src)
     d, dpl = _host_planes(dst)
     if (dpl.height, dpl.width, dpl.n_frames, dpl.pitch_bytes, dpl.frame_stride_bytes) != \
             (pl.height, pl.width, pl.n_frames, pl.pitch_bytes, pl.frame_stride_bytes):
         raise ValueError("dst must have the geometry of src")
-    packed, n = pack_bits(wm_rows)
+    if wm_len is None:
+        packed, n = pack_bits(wm_rows)
+    else:
+        packed, n = wm_rows, int(wm_len)
+        if not isinstance(packed, torch.Tensor) or packed.is_cuda or packed.dtype != torch.int32 or packed.dim() != 2 \
+                or not packed.is_contiguous():
+            raise ValueError("packed watermark rows must be a contiguous CPU int32 [rows, words] tensor")
     rows = None
     if frame_wm_row is not None:
         rows = torch.as_tensor(frame_wm_row, dtype=torch.int32).contiguous()
@@ -375,6 +401,11 @@ def dwtsvd_detect_host(src, perm, scale=15.0, chunk_frames=0, want_raw_bits=Fals
     if want_raw_bits:
         return patterns.numpy(), raw[:, :words].numpy().view(np.uint32)
     return patterns.numpy()
+
+
+def host_scratch_release():
+    """Free the streams and device scratch that the host-buffer entry points keep between calls."""
+    check(lib.b200wm_host_scratch_release())
 
 
 # ----------------------------------------------------------------------------- distortion channel

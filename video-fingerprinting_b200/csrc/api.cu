@@ -37,6 +37,7 @@ int launch_embed_rgb8(const uint8_t*, uint8_t*, int, int, int, long long, long l
 int launch_extract_rgb8(const uint8_t*, int, int, int, long long, long long, int, float, uint32_t*, int, int, int32_t*, cudaStream_t);
 int mark_host(const uint8_t*, uint8_t*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float, int);
 int detect_host(const uint8_t*, const b200wm_plane*, float, int, const int32_t*, uint8_t*, uint32_t*, int32_t*, int);
+int host_scratch_release();
 void set_path(int);
 int get_path();
 int launch_yuv32_to_bgr8(const float*, uint8_t*, long long, cudaStream_t);
@@ -165,6 +166,8 @@ B200WM_API int b200wm_bgr8_to_yuv32(const uint8_t* bgr, float* yuv, int64_t n_pi
 B200WM_API int b200wm_yuv32_to_bgr8(const float* yuv, uint8_t* bgr, int64_t n_pixels, void* stream) {
     return launch_yuv32_to_bgr8(yuv, bgr, n_pixels, (cudaStream_t)stream);
 }
+
+B200WM_API int b200wm_host_scratch_release(void) { return host_scratch_release(); }
 
 B200WM_API int b200wm_attack_jpeg_requant(const void* src, void* dst, const b200wm_plane* plane, int32_t quality, void* stream) {
     return launch_attack_jpeg(src, dst, plane, quality, (cudaStream_t)stream);

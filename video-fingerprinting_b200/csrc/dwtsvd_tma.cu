@@ -20,7 +20,10 @@
 //     (no CTA-wide barrier in the loop).  HBM latency is hidden by the ring depth, no consumer
 //     spends issue slots on global address arithmetic and the 64 source bytes of a tile never
 //     occupy registers for the length of the SVD.
-//   * Consumer thread t owns TWO tiles of the strip, t and t + 128, and runs the eigen-iteration for
+//   * Narrow planes (at most 128 tiles per row, e.g. the 960-wide chroma planes of 1080p yuv420p) take
+//     two tile rows per work item, so that both packed lanes of every thread stay busy.
+//   * Consumer thread t owns TWO tiles of the strip, t and t + 128 (narrow planes: tile t of the first
+//     and of the second tile row), and runs the eigen-iteration for
 //     both in packed FP32 (FFMA2/FMUL2/FADD2, svd4x2.cuh): the kernels are issue-bound, and a packed
 //     instruction does the work of two for one issue slot.  It reads its 8x8 bytes from shared memory
 //     (conflict-free: a warp reads 256 contiguous bytes per row).  Embed updates the strip in
@@ -121,38 +124,47 @@ __device__ __forceinline__ void sts_u2_if(bool pred, unsigned addr, uint2 v) {
 // Items are numbered i = (frame * tiles_y + ty) * chunks_x + cx; CTA b processes i = b, b + grid, ...
 struct StripGeom {
     TileGeom g;
-    int total;                       // n_frames * tiles_y * chunks_x (< 2^26 so that the magic divisions are exact)
+    int total;                       // n_frames * frame_items (< 2^26 so that the magic divisions are exact)
     int chunks_x;                    // column chunks per tile row (1 up to 256 tiles per row)
     int chunk_tiles;                 // tiles per chunk, even; the last chunk of a row may hold fewer
-    int frame_items;                 // tiles_y * chunks_x
+    int frame_items;                 // work items per frame: tiles_y * chunks_x, or ceil(tiles_y / 2) on narrow planes
     unsigned long long frame_magic;  // i / frame_items == (i * magic) >> 40
     unsigned long long chunk_magic;  // j / chunks_x    == (j * magic) >> 40
     unsigned pitch;                  // row pitch of the plane in global memory
     unsigned slot_pitch;             // row pitch of a strip in shared memory = 8 * chunk_tiles
-    unsigned slot_bytes;             // 8 * slot_pitch
+    unsigned slot_bytes;             // 8 (narrow planes: 16) * slot_pitch
     int whole;                       // 1: the strip is contiguous in global memory too -> one bulk copy
+    int narrow;                      // 1: two tile rows per item
     long long frame_stride;
 };
 
 struct Item {
-    int frame, ty, cx, tiles;        // tiles = tiles of this chunk
+    int frame, ty, cx, tiles, rows;  // tiles = tiles of this chunk; rows = tile rows of this item (narrow planes: 1 or 2)
 };
 
 // kWhole: one chunk per tile row and tight rows (the 1080p case) - a strip is contiguous in global
 // memory, moves with a single bulk copy, and the item index needs one division only.
-template <bool kWhole>
+// kNarrow: tiles_x <= 128 - an item is two consecutive tile rows (one at the bottom of an odd plane).
+template <bool kWhole, bool kNarrow>
 __device__ __forceinline__ Item item_of(int i, const StripGeom& sg) {
     Item it;
     it.frame = (int)(((unsigned long long)(unsigned)i * sg.frame_magic) >> 40);
     const int j = i - it.frame * sg.frame_items;
-    if (kWhole) {
+    if (kNarrow) {
+        it.ty = 2 * j;
+        it.cx = 0;
+        it.tiles = sg.g.tiles_x;
+        it.rows = min(2, sg.g.tiles_y - it.ty);
+    } else if (kWhole) {
         it.ty = j;
         it.cx = 0;
         it.tiles = sg.g.tiles_x;
+        it.rows = 1;
     } else {
         it.ty = (int)(((unsigned long long)(unsigned)j * sg.chunk_magic) >> 40);
         it.cx = j - it.ty * sg.chunks_x;
         it.tiles = min(sg.chunk_tiles, sg.g.tiles_x - it.cx * sg.chunk_tiles);
+        it.rows = 1;
     }
     return it;
 }
@@ -177,39 +189,63 @@ __device__ __forceinline__ void init_ring(unsigned full0, unsigned done0) {
 }
 
 // Called by the whole (converged) producer warp: lane 0 arms the barrier, then it moves the whole
-// strip (kWhole) or eight lanes move one sample row each.
-template <bool kWhole>
+// strip (kWhole) or 8 (16) lanes move one sample row each.
+template <bool kWhole, bool kNarrow>
 __device__ __forceinline__ void load_item(const uint8_t* src, int i, unsigned slot, unsigned bar, const StripGeom& sg, int lane) {
+    const Item it = item_of<kWhole, kNarrow>(i, sg);
+    const unsigned row_bytes = (unsigned)it.tiles * 8u, n_rows = 8u * (unsigned)it.rows;
     if (kWhole) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(bar, sg.slot_bytes);
-            bulk_load(slot, src + item_offset(item_of<true>(i, sg), sg), sg.slot_bytes, bar);
+            mbar_arrive_expect_tx(bar, n_rows * row_bytes);
+            bulk_load(slot, src + item_offset(it, sg), n_rows * row_bytes, bar);
         }
         return;
     }
-    const Item it = item_of<false>(i, sg);
-    const unsigned row_bytes = (unsigned)it.tiles * 8u;
-    if (lane == 0) mbar_arrive_expect_tx(bar, 8u * row_bytes);
+    if (lane == 0) mbar_arrive_expect_tx(bar, n_rows * row_bytes);
     __syncwarp();
-    if (lane < 8)
+    if ((unsigned)lane < n_rows)
         bulk_load(slot + lane * sg.slot_pitch, src + item_offset(it, sg) + (unsigned long long)lane * sg.pitch, row_bytes, bar);
 }
 
-template <bool kWhole>
+template <bool kWhole, bool kNarrow>
 __device__ __forceinline__ void store_item(uint8_t* dst, int i, unsigned slot, const StripGeom& sg, int lane) {
+    const Item it = item_of<kWhole, kNarrow>(i, sg);
+    const unsigned row_bytes = (unsigned)it.tiles * 8u, n_rows = 8u * (unsigned)it.rows;
     if (kWhole) {
-        if (lane == 0) bulk_store(dst + item_offset(item_of<true>(i, sg), sg), slot, sg.slot_bytes);
-    } else {
-        const Item it = item_of<false>(i, sg);
-        if (lane < 8)
-            bulk_store(dst + item_offset(it, sg) + (unsigned long long)lane * sg.pitch, slot + lane * sg.slot_pitch, (unsigned)it.tiles * 8u);
+        if (lane == 0) bulk_store(dst + item_offset(it, sg), slot, n_rows * row_bytes);
+    } else if ((unsigned)lane < n_rows) {
+        bulk_store(dst + item_offset(it, sg) + (unsigned long long)lane * sg.pitch, slot + lane * sg.slot_pitch, row_bytes);
     }
     bulk_commit();
 }
 
+// The two tiles of consumer thread t in an item: shared-memory byte offsets (dead lanes read tile 0 and
+// are masked later), liveness, and the distance between their block indices.
+template <bool kNarrow>
+struct TilePair {
+    bool live_lo, live_hi, warp_live_lo, warp_live_hi;
+    unsigned off_lo, off_hi, hi_delta;
+    __device__ __forceinline__ TilePair(int t, const Item& it, const StripGeom& sg) {
+        live_lo = t < it.tiles;
+        warp_live_lo = (t & ~31) < it.tiles;
+        if (kNarrow) {
+            live_hi = live_lo && it.rows == 2;
+            warp_live_hi = warp_live_lo && it.rows == 2;
+            hi_delta = (unsigned)sg.g.tiles_x;
+            off_hi = live_hi ? 8u * sg.slot_pitch + (unsigned)t * 8u : 0u;
+        } else {
+            live_hi = t + kStripThreads < it.tiles;
+            warp_live_hi = ((t + kStripThreads) & ~31) < it.tiles;
+            hi_delta = kStripThreads;
+            off_hi = live_hi ? (unsigned)(t + kStripThreads) * 8u : 0u;
+        }
+        off_lo = live_lo ? (unsigned)t * 8u : 0u;
+    }
+};
+
 // ---- extract -------------------------------------------------------------------------------------------
 // raw_bits must be zero on entry (the launcher clears it): warps OR their bits in.
-template <bool kWhole>
+template <bool kWhole, bool kNarrow>
 __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src,
                                                                                                ExtractArgs ex, StripGeom sg) {
     constexpr int kStages = kExtractStages;
@@ -232,32 +268,30 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
 #pragma unroll
         for (int s = 0; s < kStages; ++s)
             if ((int)blockIdx.x + s * step < sg.total)
-                load_item<kWhole>(src, (int)blockIdx.x + s * step, ring + s * sg.slot_bytes, full0 + 8 * s, sg, lane);
+                load_item<kWhole, kNarrow>(src, (int)blockIdx.x + s * step, ring + s * sg.slot_bytes, full0 + 8 * s, sg, lane);
         for (int i = (int)blockIdx.x; i < sg.total; i += step) {
             mbar_wait(done0 + 8 * stage, parity);        // every consumer warp is done with this slot
             if (ex.pos_counts && lane < L) {
                 const int n = cta_counts[stage][lane];
                 if (n) {
-                    atomicAdd(&ex.pos_counts[(long long)item_of<kWhole>(i, sg).frame * L + lane], n);
+                    atomicAdd(&ex.pos_counts[(long long)item_of<kWhole, kNarrow>(i, sg).frame * L + lane], n);
                     cta_counts[stage][lane] = 0;
                 }
             }
             __syncwarp();
             if (i + kStages * step < sg.total)
-                load_item<kWhole>(src, i + kStages * step, ring + stage * sg.slot_bytes, full0 + 8 * stage, sg, lane);
+                load_item<kWhole, kNarrow>(src, i + kStages * step, ring + stage * sg.slot_bytes, full0 + 8 * stage, sg, lane);
             if (++stage == kStages) { stage = 0; parity ^= 1u; }
         }
         return;
     }
 
     // ===== consumer warps =====
-    const int t = threadIdx.x, t_hi = t + kStripThreads;        // the launcher guarantees chunk_tiles <= 2 * kStripThreads
+    const int t = threadIdx.x;                                   // the launcher guarantees chunk_tiles <= 2 * kStripThreads
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
-        const Item it = item_of<kWhole>(i, sg);
+        const Item it = item_of<kWhole, kNarrow>(i, sg);
         const unsigned slot = ring + stage * sg.slot_bytes;
-        const bool live_lo = t < it.tiles, live_hi = t_hi < it.tiles;
-        const bool warp_live_lo = (t & ~31) < it.tiles, warp_live_hi = (t_hi & ~31) < it.tiles;     // warp-uniform
-        const unsigned off_lo = (live_lo ? t : 0) * 8, off_hi = (live_hi ? t_hi : 0) * 8;           // dead lanes read tile 0
+        const TilePair<kNarrow> tp(t, it, sg);
         mbar_wait(full0 + 8 * stage, parity);
         unsigned bits;
         {
@@ -266,34 +300,41 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
                 uint2 ra[8], rb[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    ra[r] = lds_u2(slot + r * sg.slot_pitch + off_lo);
-                    rb[r] = lds_u2(slot + r * sg.slot_pitch + off_hi);
+                    ra[r] = lds_u2(slot + r * sg.slot_pitch + tp.off_lo);
+                    rb[r] = lds_u2(slot + r * sg.slot_pitch + tp.off_hi);
                 }
                 sums_from_rows_x2(ra, rb, S);
             }
             bits = extract_bits_x2(S, ex.scale, ex.inv_scale);
         }
-        const unsigned ballot_lo = __ballot_sync(0xFFFFFFFFu, live_lo && (bits & 1u));
-        const unsigned ballot_hi = __ballot_sync(0xFFFFFFFFu, live_hi && (bits & 2u));
+        const unsigned ballot_lo = __ballot_sync(0xFFFFFFFFu, tp.live_lo && (bits & 1u));
+        const unsigned ballot_hi = __ballot_sync(0xFFFFFFFFu, tp.live_hi && (bits & 2u));
         const unsigned c0 = (unsigned)(it.ty * g.tiles_x + it.cx * sg.chunk_tiles + (t & ~31));     // first block of the low half
+        const unsigned c1 = c0 + tp.hi_delta;                                                       // ... of the high half
         if (lane == 0) {
             uint32_t* frame_bits = ex.raw_bits + (long long)it.frame * g.words;
-            if (warp_live_lo && ballot_lo) {
+            if (tp.warp_live_lo && ballot_lo) {
                 const unsigned sh = c0 & 31u;
                 atomicOr(frame_bits + (c0 >> 5), ballot_lo << sh);
                 if (sh && (ballot_lo >> (32u - sh))) atomicOr(frame_bits + (c0 >> 5) + 1, ballot_lo >> (32u - sh));
             }
-            if (warp_live_hi && ballot_hi) {
-                const unsigned c1 = c0 + kStripThreads, sh = c1 & 31u;
+            if (tp.warp_live_hi && ballot_hi) {
+                const unsigned sh = c1 & 31u;
                 atomicOr(frame_bits + (c1 >> 5), ballot_hi << sh);
                 if (sh && (ballot_hi >> (32u - sh))) atomicOr(frame_bits + (c1 >> 5) + 1, ballot_hi >> (32u - sh));
             }
         }
         if (ex.pos_counts && lane < L) {
-            // lane i sees the bits of blocks c0+i, c0+i+L, ... of both halves (128 is a multiple of L):
-            // payload position (c0 + i) mod L
-            const int n = __popc(ballot_lo & (ex.every << lane)) + __popc(ballot_hi & (ex.every << lane));
-            if (n) atomicAdd(&cta_counts[stage][(c0 + lane) & (unsigned)(L - 1)], n);
+            // lane i sees the bits of blocks c+i, c+i+L, ...: payload position (c + i) mod L.  The halves are
+            // 128 blocks apart (a multiple of L) except on narrow planes, where they are one tile row apart.
+            if (kNarrow) {
+                const int n0 = __popc(ballot_lo & (ex.every << lane)), n1 = __popc(ballot_hi & (ex.every << lane));
+                if (n0) atomicAdd(&cta_counts[stage][(c0 + lane) & (unsigned)(L - 1)], n0);
+                if (n1) atomicAdd(&cta_counts[stage][(c1 + lane) & (unsigned)(L - 1)], n1);
+            } else {
+                const int n = __popc(ballot_lo & (ex.every << lane)) + __popc(ballot_hi & (ex.every << lane));
+                if (n) atomicAdd(&cta_counts[stage][(c0 + lane) & (unsigned)(L - 1)], n);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(done0 + 8 * stage);
@@ -302,7 +343,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
 }
 
 // ---- embed ----------------------------------------------------------------------------------------------
-template <bool kWhole>
+template <bool kWhole, bool kNarrow>
 __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                       EmbedArgs em, StripGeom sg) {
     constexpr int kStages = kEmbedStages;
@@ -324,16 +365,16 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
 #pragma unroll
         for (int s = 0; s < kStages - 1; ++s)            // the last slot is filled by the first refill
             if ((int)blockIdx.x + s * step < sg.total)
-                load_item<kWhole>(src, (int)blockIdx.x + s * step, ring + s * sg.slot_bytes, full0 + 8 * s, sg, lane);
+                load_item<kWhole, kNarrow>(src, (int)blockIdx.x + s * step, ring + s * sg.slot_bytes, full0 + 8 * s, sg, lane);
         int refill = kStages - 1;
         for (int i = (int)blockIdx.x; i < sg.total; i += step) {
             mbar_wait(done0 + 8 * stage, parity);        // every consumer warp has rewritten its tiles of this strip
-            store_item<kWhole>(dst, i, ring + stage * sg.slot_bytes, sg, lane);
+            store_item<kWhole, kNarrow>(dst, i, ring + stage * sg.slot_bytes, sg, lane);
             // the slot stored one iteration ago has been read by now (every lane: at most its newest store pending)
             bulk_wait_read<1>();
             if (!kWhole) __syncwarp();
             const int nxt = i + (kStages - 1) * step;    // the strip kStages-1 iterations ahead
-            if (nxt < sg.total) load_item<kWhole>(src, nxt, ring + refill * sg.slot_bytes, full0 + 8 * refill, sg, lane);
+            if (nxt < sg.total) load_item<kWhole, kNarrow>(src, nxt, ring + refill * sg.slot_bytes, full0 + 8 * refill, sg, lane);
             refill = stage;
             if (++stage == kStages) { stage = 0; parity ^= 1u; }
         }
@@ -342,12 +383,11 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
     }
 
     // ===== consumer warps =====
-    const int t = threadIdx.x, t_hi = t + kStripThreads;        // the launcher guarantees chunk_tiles <= 2 * kStripThreads
+    const int t = threadIdx.x;                                   // the launcher guarantees chunk_tiles <= 2 * kStripThreads
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
-        const Item it = item_of<kWhole>(i, sg);
+        const Item it = item_of<kWhole, kNarrow>(i, sg);
         const unsigned slot = ring + stage * sg.slot_bytes;
-        const bool live_lo = t < it.tiles, live_hi = t_hi < it.tiles;
-        const unsigned off_lo = (live_lo ? t : 0) * 8, off_hi = (live_hi ? t_hi : 0) * 8;           // dead lanes read tile 0
+        const TilePair<kNarrow> tp(t, it, sg);
         // the watermark bits of this warp's tiles (32 per half), funnel-shifted out of the packed row;
         // issued before the wait so that their latency hides behind it
         const int row = em.frame_row ? em.frame_row[it.frame] : 0;
@@ -356,7 +396,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
         unsigned wbits[2];
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
-            const unsigned c = c0 + hlf * kStripThreads;
+            const unsigned c = c0 + hlf * tp.hi_delta;
             const int wi = (int)(c >> 5);
             wbits[hlf] = 0u;
             if (wi < em.wm_words) {
@@ -367,7 +407,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
         const unsigned mybits = ((wbits[0] >> lane) & 1u) | (((wbits[1] >> lane) & 1u) << 1);
         mbar_wait(full0 + 8 * stage, parity);
         {
-            const unsigned mine_lo = slot + off_lo, mine_hi = slot + off_hi;
+            const unsigned mine_lo = slot + tp.off_lo, mine_hi = slot + tp.off_hi;
             f2 D[16];
             {
                 f2 S[16];
@@ -391,8 +431,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const unsigned ro = (2 * i2 + rr) * sg.slot_pitch;
-                    sts_u2_if(live_lo, mine_lo + ro, add_clamp_row(lds_u2(mine_lo + ro), a01, a23));
-                    sts_u2_if(live_hi, mine_hi + ro, add_clamp_row(lds_u2(mine_hi + ro), b01, b23));
+                    sts_u2_if(tp.live_lo, mine_lo + ro, add_clamp_row(lds_u2(mine_lo + ro), a01, a23));
+                    sts_u2_if(tp.live_hi, mine_hi + ro, add_clamp_row(lds_u2(mine_hi + ro), b01, b23));
                 }
             }
         }
@@ -419,7 +459,7 @@ bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const Ti
         return false;
     if (pl->n_frames > 1 && pl->frame_stride_bytes < pl->pitch_bytes * (long long)pl->height) return false;
     int chunk_tiles = 0;
-    const long long frame_items = (long long)g.tiles_y * strip_chunks(g, &chunk_tiles);
+    const long long frame_items = (long long)g.tiles_y * strip_chunks(g, &chunk_tiles);     // (narrow planes: about half of it)
     const long long items = pl->n_frames * frame_items;
     return items < (1ll << 26) && items * frame_items < (1ll << 40);     // exact magic divisions
 }
@@ -444,45 +484,57 @@ static StripGeom make_strip_geom(const TileGeom& g, const b200wm_plane* pl) {
     StripGeom sg;
     sg.g = g;
     sg.chunks_x = strip_chunks(g, &sg.chunk_tiles);
-    sg.frame_items = g.tiles_y * sg.chunks_x;
+    sg.narrow = g.tiles_x <= kStripThreads ? 1 : 0;
+    sg.frame_items = sg.narrow ? (g.tiles_y + 1) / 2 : g.tiles_y * sg.chunks_x;
     sg.total = pl->n_frames * sg.frame_items;
     sg.frame_magic = (1ull << 40) / (unsigned long long)sg.frame_items + 1ull;
     sg.chunk_magic = (1ull << 40) / (unsigned long long)sg.chunks_x + 1ull;
     sg.pitch = (unsigned)pl->pitch_bytes;
     sg.slot_pitch = 8u * (unsigned)sg.chunk_tiles;
-    sg.slot_bytes = 8u * sg.slot_pitch;
+    sg.slot_bytes = (sg.narrow ? 16u : 8u) * sg.slot_pitch;
     sg.whole = (sg.chunks_x == 1 && sg.slot_pitch == sg.pitch) ? 1 : 0;
     sg.frame_stride = pl->frame_stride_bytes;
     return sg;
 }
 
-int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const TileGeom& g, ExtractArgs xa, cudaStream_t stream) {
-    const StripGeom sg = make_strip_geom(g, pl);
+template <bool kWhole, bool kNarrow>
+static int launch_extract_t(const uint8_t* src, const ExtractArgs& xa, const StripGeom& sg, cudaStream_t stream) {
     const size_t smem = (size_t)kExtractStages * sg.slot_bytes;
     int blocks = 0;
-    int rc = sg.whole ? persistent_grid(dwtsvd_extract_tma_kernel<true>, smem, &blocks)
-                      : persistent_grid(dwtsvd_extract_tma_kernel<false>, smem, &blocks);
+    const int rc = persistent_grid(dwtsvd_extract_tma_kernel<kWhole, kNarrow>, smem, &blocks);
     if (rc) return rc;
     if (sg.total < blocks) blocks = sg.total;
-    if (sg.whole) dwtsvd_extract_tma_kernel<true><<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, xa, sg);
-    else dwtsvd_extract_tma_kernel<false><<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, xa, sg);
+    dwtsvd_extract_tma_kernel<kWhole, kNarrow><<<blocks, kCtaThreads, smem, stream>>>(src, xa, sg);
     B200WM_LAUNCH_CHECK("dwtsvd_extract_tma_kernel");
     return B200WM_OK;
+}
+
+template <bool kWhole, bool kNarrow>
+static int launch_embed_t(const uint8_t* src, uint8_t* dst, const EmbedArgs& ea, const StripGeom& sg, cudaStream_t stream) {
+    const size_t smem = (size_t)kEmbedStages * sg.slot_bytes;
+    int blocks = 0;
+    const int rc = persistent_grid(dwtsvd_embed_tma_kernel<kWhole, kNarrow>, smem, &blocks);
+    if (rc) return rc;
+    if (sg.total < blocks) blocks = sg.total;
+    dwtsvd_embed_tma_kernel<kWhole, kNarrow><<<blocks, kCtaThreads, smem, stream>>>(src, dst, ea, sg);
+    B200WM_LAUNCH_CHECK("dwtsvd_embed_tma_kernel");
+    return B200WM_OK;
+}
+
+int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const TileGeom& g, ExtractArgs xa, cudaStream_t stream) {
+    const StripGeom sg = make_strip_geom(g, pl);
+    const uint8_t* p = (const uint8_t*)src;
+    if (sg.narrow) return sg.whole ? launch_extract_t<true, true>(p, xa, sg, stream) : launch_extract_t<false, true>(p, xa, sg, stream);
+    return sg.whole ? launch_extract_t<true, false>(p, xa, sg, stream) : launch_extract_t<false, false>(p, xa, sg, stream);
 }
 
 int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, const TileGeom& g, EmbedArgs ea,
                             cudaStream_t stream) {
     const StripGeom sg = make_strip_geom(g, pl);
-    const size_t smem = (size_t)kEmbedStages * sg.slot_bytes;
-    int blocks = 0;
-    int rc = sg.whole ? persistent_grid(dwtsvd_embed_tma_kernel<true>, smem, &blocks)
-                      : persistent_grid(dwtsvd_embed_tma_kernel<false>, smem, &blocks);
-    if (rc) return rc;
-    if (sg.total < blocks) blocks = sg.total;
-    if (sg.whole) dwtsvd_embed_tma_kernel<true><<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea, sg);
-    else dwtsvd_embed_tma_kernel<false><<<blocks, kCtaThreads, smem, stream>>>((const uint8_t*)src, (uint8_t*)dst, ea, sg);
-    B200WM_LAUNCH_CHECK("dwtsvd_embed_tma_kernel");
-    return B200WM_OK;
+    const uint8_t* p = (const uint8_t*)src;
+    uint8_t* d = (uint8_t*)dst;
+    if (sg.narrow) return sg.whole ? launch_embed_t<true, true>(p, d, ea, sg, stream) : launch_embed_t<false, true>(p, d, ea, sg, stream);
+    return sg.whole ? launch_embed_t<true, false>(p, d, ea, sg, stream) : launch_embed_t<false, false>(p, d, ea, sg, stream);
 }
 
 }  // namespace b200wm
