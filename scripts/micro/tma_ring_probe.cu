@@ -71,31 +71,33 @@ __global__ void __launch_bounds__(kThreads) ring_kernel(const uint8_t* src, uint
 }
 
 int main() {
-    const unsigned strip = 15360;
-    const int frames = 3000, strips_per_frame = 135;
-    const size_t bytes = (size_t)frames * strips_per_frame * strip;     // 6.2 GB, like the Y planes of the bench
+    const size_t bytes = (size_t)3000 * 135 * 15360;     // 6.2 GB, like the Y planes of the bench
     uint8_t *a, *b; unsigned* sink;
     cudaMalloc(&a, bytes); cudaMalloc(&b, bytes); cudaMalloc(&sink, 4);
     cudaMemset(a, 1, bytes); cudaMemset(b, 2, bytes);
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const size_t smem = kStages * strip;
-    cudaFuncSetAttribute(ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int per_sm = 2; per_sm <= 4; ++per_sm) {
-        for (int mode = 0; mode < 2; ++mode) {
-            const int total = frames * strips_per_frame, blocks = sms * per_sm;
-            auto launch = [&] {
-                if (mode) ring_kernel<true><<<blocks, kThreads, smem>>>(a, b, total, strip, sink);
-                else ring_kernel<false><<<blocks, kThreads, smem>>>(a, b, total, strip, sink);
-            };
-            launch(); launch();
-            cudaEventRecord(e0);
-            for (int r = 0; r < 5; ++r) launch();
-            cudaEventRecord(e1); cudaEventSynchronize(e1);
-            float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-            printf("%s  %d CTAs/SM: %.3f ms  %.0f GB/s %s\n", mode ? "copy" : "read", per_sm, ms, (mode ? 2.0 : 1.0) * bytes / ms * 1e-6,
-                   cudaGetLastError() == cudaSuccess ? "" : "ERROR");
+    const unsigned strips[] = {7680, 15360, 30720};
+    for (unsigned strip : strips) {
+        const size_t smem = kStages * strip;
+        cudaFuncSetAttribute(ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        for (int per_sm = 1; per_sm <= 8; ++per_sm) {
+            if ((smem + 1024) * per_sm > 227 * 1024) break;
+            for (int mode = 0; mode < 2; ++mode) {
+                const int total = (int)(bytes / strip), blocks = sms * per_sm;
+                auto launch = [&] {
+                    if (mode) ring_kernel<true><<<blocks, kThreads, smem>>>(a, b, total, strip, sink);
+                    else ring_kernel<false><<<blocks, kThreads, smem>>>(a, b, total, strip, sink);
+                };
+                launch(); launch();
+                cudaEventRecord(e0);
+                for (int r = 0; r < 5; ++r) launch();
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+                printf("%s  strip %5u B  %d CTAs/SM (%3zu KB in the rings per SM): %.3f ms  %.0f GB/s %s\n", mode ? "copy" : "read", strip, per_sm,
+                       smem * per_sm / 1024, ms, (mode ? 2.0 : 1.0) * bytes / ms * 1e-6, cudaGetLastError() == cudaSuccess ? "" : "ERROR");
+            }
         }
     }
     // plain device-to-device memcpy for reference
