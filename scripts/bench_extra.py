@@ -111,6 +111,18 @@ def main():
     report("dct8 embed (U read+write)", ms_e, n, 8 * h * w)
     report("dct8 extract (U read)", ms_x, n, 4 * h * w)
     del yuv
+    # ---- the same pair on planar uint8 (yuv444 planes): masks from Y, mark in the U plane
+    n = 512
+    yp = planes(n, h, w, seed=5)
+    up = planes(n, h, w, seed=6)
+    ms_m = timed(lambda: ops.dct8_masks(yp))
+    masks = ops.dct8_masks(yp)
+    ms_e = timed(lambda: ops.dct8_embed_(up, masks, wm, ln, alpha=20))
+    ms_x = timed(lambda: ops.dct8_extract(up, masks, alpha=20, payload_len=8))
+    report("dct8 masks (planar uint8, Y read)", ms_m, n, h * w)
+    report("dct8 embed (planar uint8, U read+write)", ms_e, n, 2 * h * w)
+    report("dct8 extract (planar uint8, U read)", ms_x, n, h * w)
+    del yp, up
     # ---- attack kernels
     y = planes(512, h, w)
     report("jpeg-like requant q75 (in place)", timed(lambda: ops.attack_jpeg_requant_(y, 75)), 512, 2 * h * w)

@@ -85,3 +85,52 @@ def test_dct8_embed_extract_vs_oracle(golden_dir, source):
     assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), o_pay.degenerate(bits_ref, 8, KEY))
     assert np.array_equal(o_pay.degenerate(o_dct.decode(got.copy()), 8, KEY), PAYLOAD)
     assert counts[0].cpu().tolist() == [int(bits[0][i::8].sum()) for i in range(8)]
+
+
+def test_dct8_uint8_planes_fast_path_vs_generic_and_oracle():
+    """Planar uint8 (yuv444 planes): the vector-load instantiations (8-byte aligned rows) give the same
+    masks, bytes and bits as the generic byte-wise ones (unaligned view), and the marked plane equals the
+    reference flow on the same values (float YUV -> DctEncoder -> clip/around, dct_encoder.py:18-39 +
+    video/embedder.py:37-38) within 1 LSB wherever the sign of c21 is not float32 noise."""
+    from b200wm import ops
+    h, w = 136, 200
+    rng = np.random.RandomState(77)
+    base = synth.random_bgr(h, w, 5)
+    yp = base[:, :, 0].copy()
+    up = np.clip(base[:, :, 1].astype(np.int16) + rng.randint(-3, 4, (h, w)), 0, 255).astype(np.uint8)
+    up[:16, :16] = 255                      # saturated and flat blocks (c21 == 0 exactly: stay unmarked)
+    up[16:24, :8] = 0
+    wm = o_pay.generate_wm(PAYLOAD, (1, h * w // 64), KEY)
+    packed, n = ops.pack_bits(wm[0], device=DEV)
+
+    def run(aligned):
+        if aligned:
+            ty, tu = torch.from_numpy(yp.copy()).to(DEV), torch.from_numpy(up.copy()).to(DEV)
+        else:
+            big = torch.zeros((2, h + 1, w + 11), dtype=torch.uint8, device=DEV)
+            ty, tu = big[0, 1:, 3:w + 3], big[1, 1:, 3:w + 3]
+            ty.copy_(torch.from_numpy(yp)); tu.copy_(torch.from_numpy(up))
+        masks = ops.dct8_masks(ty)
+        ops.dct8_embed_(tu, masks, packed, n, alpha=20)
+        raw, counts = ops.dct8_extract(tu, masks, alpha=20, payload_len=8)
+        return [m.cpu().numpy() for m in masks], tu.cpu().numpy(), raw.cpu().numpy(), counts.cpu().numpy()
+    m_a, u_a, raw_a, cnt_a = run(True)
+    m_g, u_g, raw_g, cnt_g = run(False)
+    for a, b in zip(m_a, m_g):
+        assert np.array_equal(a, b)
+    assert np.array_equal(u_a, u_g) and np.array_equal(raw_a, raw_g) and np.array_equal(cnt_a, cnt_g)
+    # reference flow on the same values
+    yuv = np.zeros((h, w, 3), dtype=np.float32)
+    yuv[:, :, 0], yuv[:, :, 1] = yp, up
+    want = np.around(np.clip(o_dct.encode(yuv.copy(), wm)[:, :, 1], 0, 255)).astype(np.uint8)
+    by, bx = h // 8, w // 8
+    c21 = o_dct._dct_all(yuv[:, :, 1])[..., 2, 1]
+    err = np.abs(u_a[:by * 8, :bx * 8].astype(np.int16) - want[:by * 8, :bx * 8]).reshape(by, 8, bx, 8).max(axis=(1, 3))
+    solid = np.abs(c21) > 1e-3
+    assert (err[solid] <= 1).mean() > 0.995, (err[solid] <= 1).mean()        # tolerance: 1 LSB
+    assert np.array_equal(u_a[by * 8:], up[by * 8:]) and np.array_equal(u_a[:, bx * 8:], up[:, bx * 8:])
+    # and the payload reads back, by us and by the reference decoder
+    bits = ops.unpack_bits(torch.from_numpy(raw_a), h * w // 64)
+    assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), PAYLOAD)
+    yuv[:, :, 1] = u_a
+    assert np.array_equal(o_pay.degenerate(o_dct.decode(yuv), 8, KEY), PAYLOAD)

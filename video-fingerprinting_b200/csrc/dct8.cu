@@ -32,6 +32,41 @@ __device__ __forceinline__ void load_block(const uint8_t* p, long long pitch, in
     }
 }
 
+// Fast path for planar uint8 with 8-byte aligned rows: eight 64-bit loads per block, and every byte
+// becomes a float by PRMT into the mantissa of 1.5 * 2^23 (value 12582912 + byte, exact) - no
+// byte loads, no I2F.  Differences of two such values are the exact sample differences, and an FMA
+// that adds a small increment to one rounds sample + increment to the nearest integer (ties to even)
+// and leaves it in the low mantissa bits, ready for the 16-bit saturating pack below.
+constexpr unsigned kBiasBits = 0x4B400000u;
+constexpr float kBias = 12582912.0f;
+
+__device__ __forceinline__ void load_rows_u8(const uint8_t* p, long long pitch, uint2 (&rows)[8]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) rows[y] = ldg_stream_u2(p + y * pitch);
+}
+template <int kByte>
+__device__ __forceinline__ float biased_byte(unsigned w) {
+    return __uint_as_float(__byte_perm(w, kBiasBits, 0x7640 | kByte));
+}
+// b[8*y + x] = kBias + sample
+__device__ __forceinline__ void biased_block(const uint2 (&rows)[8], float (&b)[64]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        b[8 * y + 0] = biased_byte<0>(rows[y].x); b[8 * y + 1] = biased_byte<1>(rows[y].x);
+        b[8 * y + 2] = biased_byte<2>(rows[y].x); b[8 * y + 3] = biased_byte<3>(rows[y].x);
+        b[8 * y + 4] = biased_byte<0>(rows[y].y); b[8 * y + 5] = biased_byte<1>(rows[y].y);
+        b[8 * y + 6] = biased_byte<2>(rows[y].y); b[8 * y + 7] = biased_byte<3>(rows[y].y);
+    }
+}
+// eight floats holding kBias + integer -> eight bytes clamped to [0, 255]
+__device__ __forceinline__ uint2 pack_biased_row(const float (&f)[8]) {
+    unsigned lanes[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        lanes[k] = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(f[2 * k]), __float_as_uint(f[2 * k + 1]), 0x5410), 0u, 0x00FF00FFu);
+    return make_uint2(__byte_perm(lanes[0], lanes[1], 0x6420), __byte_perm(lanes[2], lanes[3], 0x6420));
+}
+
 struct BlockGeom {
     int bx, by, nb;                 // 8x8 blocks per row / column / frame
     unsigned long long div_magic;   // c / bx == (c * magic) >> 40
@@ -90,7 +125,7 @@ __device__ __forceinline__ float texture_mask(const float (&c)[64]) {
     return mask;
 }
 
-template <typename T>
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(kDctThreads) dct8_masks_kernel(DctPlane pl, BlockGeom g, float* __restrict__ block_mean,
                                                                  float* __restrict__ tex_mask,
                                                                  double* __restrict__ frame_sum, int frame0) {
@@ -103,7 +138,15 @@ __global__ void __launch_bounds__(kDctThreads) dct8_masks_kernel(DctPlane pl, Bl
         const uint8_t* p = pl.src + frame * pl.frame_stride + (long long)(by * 8) * pl.pitch +
                            (long long)bx * 8 * pl.elem_stride * (long long)sizeof(T);
         float b[64];
-        load_block<T>(p, pl.pitch, pl.elem_stride, b);
+        if (kVec) {
+            uint2 rows[8];
+            load_rows_u8(p, pl.pitch, rows);
+            biased_block(rows, b);
+#pragma unroll
+            for (int k = 0; k < 64; ++k) b[k] -= kBias;
+        } else {
+            load_block<T>(p, pl.pitch, pl.elem_stride, b);
+        }
         dct8x8(b);
         const float mean = b[0] * 0.125f;                  // mask[i][j] = coeffs[0][0]; mask /= 8
         const long long o = (long long)frame * g.nb + c;
@@ -160,7 +203,7 @@ struct DctWm {
     double alpha;
 };
 
-template <typename T>
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(kDctThreads) dct8_embed_kernel(DctPlane pl, BlockGeom g, const float* __restrict__ block_mean,
                                                                  const float* __restrict__ tex_mask,
                                                                  const double* __restrict__ frame_sum, DctWm wm, int frame0) {
@@ -172,7 +215,13 @@ __global__ void __launch_bounds__(kDctThreads) dct8_embed_kernel(DctPlane pl, Bl
     const long long boff = frame * pl.frame_stride + (long long)(by * 8) * pl.pitch +
                            (long long)bx * 8 * pl.elem_stride * (long long)sizeof(T);
     float b[64], b1[8], b2[8];
-    load_block<T>(pl.src + boff, pl.pitch, pl.elem_stride, b);
+    uint2 rows[8];
+    if (kVec) {
+        load_rows_u8(pl.src + boff, pl.pitch, rows);
+        biased_block(rows, b);                 // kBias + sample: project21 only takes differences
+    } else {
+        load_block<T>(pl.src + boff, pl.pitch, pl.elem_stride, b);
+    }
     basis21(b1, b2);
     const float c21 = project21(b, b1, b2);
 
@@ -189,6 +238,20 @@ __global__ void __launch_bounds__(kDctThreads) dct8_embed_kernel(DctPlane pl, Bl
     const float delta = c21_new - c21;
 
     uint8_t* op = pl.dst + boff;
+    if (kVec) {
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            // the biased samples are rebuilt from the 16 raw words (one PRMT each) rather than kept in 64 registers
+            const float dy = delta * b2[y];
+            const unsigned lo = rows[y].x, hi = rows[y].y;
+            float f[8] = {biased_byte<0>(lo), biased_byte<1>(lo), biased_byte<2>(lo), biased_byte<3>(lo),
+                          biased_byte<0>(hi), biased_byte<1>(hi), biased_byte<2>(hi), biased_byte<3>(hi)};
+#pragma unroll
+            for (int x = 0; x < 8; ++x) f[x] = fmaf(dy, b1[x], f[x]);             // kBias + round(sample + increment)
+            stg_stream_u2(op + y * pl.pitch, pack_biased_row(f));
+        }
+        return;
+    }
 #pragma unroll
     for (int y = 0; y < 8; ++y) {
         T* orow = reinterpret_cast<T*>(op + y * pl.pitch);
@@ -202,7 +265,7 @@ __global__ void __launch_bounds__(kDctThreads) dct8_embed_kernel(DctPlane pl, Bl
     }
 }
 
-template <typename T>
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(kDctThreads) dct8_extract_kernel(DctPlane pl, BlockGeom g, const float* __restrict__ block_mean,
                                                                    const float* __restrict__ tex_mask,
                                                                    const double* __restrict__ frame_sum, double alpha,
@@ -219,7 +282,13 @@ __global__ void __launch_bounds__(kDctThreads) dct8_extract_kernel(DctPlane pl, 
         const long long boff = frame * pl.frame_stride + (long long)(by * 8) * pl.pitch +
                                (long long)bx * 8 * pl.elem_stride * (long long)sizeof(T);
         float b[64], b1[8], b2[8];
-        load_block<T>(pl.src + boff, pl.pitch, pl.elem_stride, b);
+        if (kVec) {
+            uint2 rows[8];
+            load_rows_u8(pl.src + boff, pl.pitch, rows);
+            biased_block(rows, b);
+        } else {
+            load_block<T>(pl.src + boff, pl.pitch, pl.elem_stride, b);
+        }
         basis21(b1, b2);
         const float c21 = project21(b, b1, b2);
         const long long o = (long long)frame * g.nb + c;
@@ -252,6 +321,12 @@ int validate_plane(const b200wm_plane* pl);
 int launch_vote_counts(const uint32_t* raw_bits, int n_frames, int words_per_frame, long long block_num,
                        int payload_len, int32_t* pos_counts, cudaStream_t stream);
 
+// planar uint8 with 8-byte aligned rows: the vector-load instantiations
+static bool dct_vec_ok(const void* a, const void* b, const b200wm_plane* pl) {
+    return pl->dtype == B200WM_U8 && pl->elem_stride == 1 && (pl->pitch_bytes % 8) == 0 && (pl->frame_stride_bytes % 8) == 0 &&
+           ((uintptr_t)a % 8) == 0 && ((uintptr_t)b % 8) == 0;
+}
+
 static DctPlane make_dct_plane(const void* src, void* dst, const b200wm_plane* pl) {
     return DctPlane{(const uint8_t*)src, (uint8_t*)dst, pl->pitch_bytes, pl->frame_stride_bytes, pl->elem_stride,
                     pl->dtype == B200WM_F32};
@@ -275,8 +350,9 @@ int launch_dct8_masks(const void* lum, const b200wm_plane* pl, float* block_mean
     const DctPlane dp = make_dct_plane(lum, nullptr, pl);
     const unsigned gx = (g.nb + kDctThreads - 1) / kDctThreads;
     FOR_FRAME_CHUNKS(pl->n_frames, gx, {
-        if (dp.is_f32) dct8_masks_kernel<float><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, f0);
-        else dct8_masks_kernel<uint8_t><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, f0);
+        if (dp.is_f32) dct8_masks_kernel<float, false><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, f0);
+        else if (dct_vec_ok(lum, lum, pl)) dct8_masks_kernel<uint8_t, true><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, f0);
+        else dct8_masks_kernel<uint8_t, false><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, f0);
         B200WM_LAUNCH_CHECK("dct8_masks_kernel");
     })
     return B200WM_OK;
@@ -296,8 +372,9 @@ int launch_dct8_embed(const void* src, void* dst, const b200wm_plane* pl, const 
     const DctWm w{wm, frame_row, wm_words, (double)alpha};
     const unsigned gx = (g.nb + kDctThreads - 1) / kDctThreads;
     FOR_FRAME_CHUNKS(pl->n_frames, gx, {
-        if (dp.is_f32) dct8_embed_kernel<float><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, w, f0);
-        else dct8_embed_kernel<uint8_t><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, w, f0);
+        if (dp.is_f32) dct8_embed_kernel<float, false><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, w, f0);
+        else if (dct_vec_ok(src, dst, pl)) dct8_embed_kernel<uint8_t, true><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, w, f0);
+        else dct8_embed_kernel<uint8_t, false><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, w, f0);
         B200WM_LAUNCH_CHECK("dct8_embed_kernel");
     })
     return B200WM_OK;
@@ -323,11 +400,14 @@ int launch_dct8_extract(const void* src, const b200wm_plane* pl, const float* bl
         int32_t* pc = fused ? pos_counts : nullptr;
         FOR_FRAME_CHUNKS(pl->n_frames, gx, {
             if (dp.is_f32)
-                dct8_extract_kernel<float><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, (double)alpha,
-                                                                            raw_bits, tg.words, pc, payload_len, f0);
+                dct8_extract_kernel<float, false><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, (double)alpha,
+                                                                                   raw_bits, tg.words, pc, payload_len, f0);
+            else if (dct_vec_ok(src, src, pl))
+                dct8_extract_kernel<uint8_t, true><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, (double)alpha,
+                                                                                    raw_bits, tg.words, pc, payload_len, f0);
             else
-                dct8_extract_kernel<uint8_t><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, (double)alpha,
-                                                                              raw_bits, tg.words, pc, payload_len, f0);
+                dct8_extract_kernel<uint8_t, false><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, (double)alpha,
+                                                                                     raw_bits, tg.words, pc, payload_len, f0);
             B200WM_LAUNCH_CHECK("dct8_extract_kernel");
         })
     }
