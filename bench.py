@@ -346,7 +346,7 @@ def main():
         ops.dwtsvd_extract(dst, scale=15.0, payload_len=PAYLOAD_LEN, raw_bits=raw_bits, pos_counts=pos_counts)
         if record: e[2].record()
         patterns, packed = deg.degenerate_counts(pos_counts, block_num)
-        vote = SegmentVote(n_seg_global, PAYLOAD_LEN, dev)
+        vote = SegmentVote(n_seg_global, PAYLOAD_LEN, dev, owned=(rank * n_seg_local, n_seg_local))
         vote.add(packed, frame_segment=frame_seg, order_offset=rank * n_frames)
         vote.combine()
         if record:

@@ -95,3 +95,23 @@ def test_pattern_hist_reproduces_counter_mode():
         best, count = Counter(mine).most_common(1)[0]
         assert "".join(map(str, res[s][0])) == best and res[s][1] == count / len(mine) and res[s][3] == len(mine)
         assert res[s][2].tolist() == [sum(int(m[j]) for m in mine) for j in range(L)]
+
+
+def test_owned_block_layout_equals_general_layout():
+    """SegmentVote(owned=...) (rank-major state, global segment numbers in, one all-gather to combine) gives the
+    same per-segment results as the general layout; here as the second of two equal blocks of a 2-rank job."""
+    from b200wm.vote import SegmentVote
+    rng = np.random.RandomState(1)
+    L, per, n = 8, 5, 300
+    seg = (per + rng.randint(0, per, n)).astype(np.int32)      # this "rank" owns segments 5..9 of 10
+    pats = rng.choice([0x65, 0x9A, 0x11], size=n, p=[0.4, 0.4, 0.2])
+    packed = torch.tensor(pats, dtype=torch.int64, device=DEV)
+    fs = torch.tensor(seg, device=DEV)
+    general = SegmentVote(2 * per, L, DEV).add(packed, frame_segment=fs, order_offset=1000).result()
+    owned = SegmentVote(2 * per, L, DEV, owned=(per, per)).add(packed, frame_segment=fs, order_offset=1000).result()
+    for a, b in zip(general, owned):
+        assert (a[0] is None) == (b[0] is None) and a[1] == b[1] and a[3] == b[3] and np.array_equal(a[2], b[2])
+        if a[0] is not None:
+            assert np.array_equal(a[0], b[0])
+    with pytest.raises(ValueError):
+        SegmentVote(10, L, DEV, owned=(3, 5))

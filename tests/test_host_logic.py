@@ -132,3 +132,53 @@ def test_vote_combine_world_size_2_gloo():
         assert pattern == want_p and freq == want_f and frames == len(patterns)
         assert bit_votes == [sum((p >> (L - 1 - j)) & 1 for p in patterns) for j in range(L)]
         assert gp == want_p and gf == want_f
+
+
+def _owned_vote_worker(rank, world, port, L, per_segment, out_q):
+    from conftest import ROOT, PKG      # noqa: F401  (sets sys.path in the child)
+    from b200wm.vote import SegmentVote
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_seg = len(per_segment)
+    per = n_seg // world
+    vote = SegmentVote(n_seg, L, "cpu", owned=(rank * per, per))
+    state, first = vote._mine()
+    order = 0
+    for s in range(rank * per, (rank + 1) * per):           # whole segments live on one rank (config 4)
+        for p in per_segment[s]:
+            state["hist"][s - first, p] += 1
+            state["first_seen"][s - first, p] = min(int(state["first_seen"][s - first, p]), order)
+            state["seg_frames"][s - first] += 1
+            for j in range(L):
+                state["bit_votes"][s - first, j] += (p >> (L - 1 - j)) & 1
+            order += 1
+    vote.combine()
+    out_q.put((rank, [(None if r[0] is None else r[0].tolist(), r[1], r[2].tolist(), r[3]) for r in vote.result()]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_owned_segment_vote_combine_world_size_2_gloo():
+    """Whole segments dealt to ranks: the combine is one in-place all-gather of each rank's block and every
+    rank ends with every segment's Counter result (ties -> first seen, empty segment -> None)."""
+    L = 8
+    per_segment = [[0x9A, 0x65, 0x65, 0x9A], [0x01] * 5 + [0x02] * 3, [], [0x65, 0x65, 0x10]]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_owned_vote_worker, args=(r, 2, port, L, per_segment, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, res in got:
+        for s, pats in enumerate(per_segment):
+            pattern, freq, votes, frames = res[s]
+            if not pats:
+                assert pattern is None and freq is None and frames == 0
+                continue
+            want_p, want_f = _reference_vote(pats, L)
+            assert pattern == want_p and freq == want_f and frames == len(pats), (rank, s)
+            assert votes == [sum((p >> (L - 1 - j)) & 1 for p in pats) for j in range(L)]

@@ -8,9 +8,9 @@ patterns of a segment are joined to strings, ``Counter(...).most_common(1)`` pic
 Frames and segments shard across GPUs (one process per GPU).  Each rank accumulates, with
 ``b200wm_pattern_hist``, a histogram of patterns per segment, the earliest global frame index
 of each pattern, the per-bit vote counters and the frame counts; ``combine`` merges the ranks
-with one all-gather of the flat state (a few tens of KB over NCCL/NVLink; SUM of the counters and
-MIN of the first-seen indices are then taken locally), after which every rank can reproduce
-``most_common(1)`` exactly.
+with ONE all-gather over NCCL/NVLink - of each rank's own block when whole segments are dealt to
+ranks (nothing to reduce), else of the full state (SUM of the counters and MIN of the first-seen
+indices are then taken locally) - after which every rank can reproduce ``most_common(1)`` exactly.
 """
 from collections import Counter
 
@@ -24,53 +24,96 @@ MAX_HIST_BITS = 16
 
 
 class SegmentVote:
-    def __init__(self, n_segments, payload_len, device):
+    """Per-segment vote state on one rank.
+
+    ``owned=(first, count)`` declares that this rank only ever adds frames of the ``count`` consecutive
+    segments starting at ``first`` (whole HLS segments dealt to ranks, BASELINE config 4) and that every rank
+    owns the same number of segments in rank order.  The state is then laid out rank-major, ``add`` takes
+    GLOBAL segment numbers as before, and ``combine`` is ONE in-place all-gather of this rank's block with
+    nothing to reduce afterwards.  Without ``owned`` a segment may be split across ranks and ``combine``
+    all-gathers the full state and reduces it locally (SUM of counters, MIN of first-seen indices)."""
+
+    def __init__(self, n_segments, payload_len, device, owned=None):
         if payload_len > MAX_HIST_BITS:
             raise ValueError(f"pattern histogram supports payload_len <= {MAX_HIST_BITS}; "
                              "use gathered_pattern_vote for longer payloads")
         self.n_segments, self.payload_len = int(n_segments), int(payload_len)
         dev = torch.device(device)
         bins = 1 << self.payload_len
-        # one flat int32 buffer [hist | bit_votes | seg_frames | first_seen] so that ONE collective moves it all
-        a, b = self.n_segments * bins, self.n_segments * (bins + self.payload_len)
-        c = b + self.n_segments
-        self._flat = torch.zeros(c + self.n_segments * bins, dtype=torch.int32, device=dev)
+        self.owned = None
+        if owned is not None:
+            first, count = int(owned[0]), int(owned[1])
+            if count <= 0 or self.n_segments % count or first % count or first + count > self.n_segments:
+                raise ValueError("owned=(first, count) needs equal blocks of consecutive segments in rank order")
+            self.owned = (first, count)
+        blocks = self.n_segments // self.owned[1] if self.owned else 1
+        per = self.owned[1] if self.owned else self.n_segments           # segments per block
+        # per block one flat int32 run [hist | bit_votes | seg_frames | first_seen]: ONE collective moves a block
+        a, b = per * bins, per * (bins + self.payload_len)
+        c = b + per
+        self._block_len = c + per * bins
+        self._flat = torch.zeros(blocks * self._block_len, dtype=torch.int32, device=dev)
         self._n_sum = c
-        self.hist = self._flat[:a].view(self.n_segments, bins)
-        self.bit_votes = self._flat[a:b].view(self.n_segments, self.payload_len)
-        self.seg_frames = self._flat[b:c].view(self.n_segments)
-        self.first_seen = self._flat[c:].view(self.n_segments, bins)
+        blk = self._flat.view(blocks, self._block_len)
+        self.hist = blk[:, :a].view(blocks, per, bins)
+        self.bit_votes = blk[:, a:b].view(blocks, per, self.payload_len)
+        self.seg_frames = blk[:, b:c].view(blocks, per)
+        self.first_seen = blk[:, c:].view(blocks, per, bins)
         self.first_seen.fill_(ops.INT32_MAX)
+        if not self.owned:                # one block: the plain [n_segments, ...] views of the general mode
+            self.hist, self.bit_votes = self.hist[0], self.bit_votes[0]
+            self.seg_frames, self.first_seen = self.seg_frames[0], self.first_seen[0]
+
+    def _mine(self):
+        """State views that ``b200wm_pattern_hist`` accumulates into and the segment offset it subtracts."""
+        if not self.owned:
+            return {"hist": self.hist, "first_seen": self.first_seen, "bit_votes": self.bit_votes,
+                    "seg_frames": self.seg_frames}, 0
+        k = self.owned[0] // self.owned[1]
+        return {"hist": self.hist[k], "first_seen": self.first_seen[k], "bit_votes": self.bit_votes[k],
+                "seg_frames": self.seg_frames[k]}, self.owned[0]
 
     def _state(self):
-        return {"hist": self.hist, "first_seen": self.first_seen, "bit_votes": self.bit_votes,
-                "seg_frames": self.seg_frames}
+        return self._mine()[0]
 
     def add(self, packed, frame_segment=None, frame_order=None, order_offset=0):
-        """Accumulate per-frame packed patterns (int64 ``[N]`` from ``ops.vote_finish``) on the GPU."""
-        ops.pattern_hist(packed, self.payload_len, self.n_segments, frame_segment, frame_order, order_offset,
-                         state=self._state())
+        """Accumulate per-frame packed patterns (int64 ``[N]`` from ``ops.vote_finish``) on the GPU.
+        ``frame_segment`` holds global segment numbers (owned mode: all inside this rank's block)."""
+        state, first = self._mine()
+        n_seg = self.owned[1] if self.owned else self.n_segments
+        if first and frame_segment is not None:
+            frame_segment = frame_segment - first
+        ops.pattern_hist(packed, self.payload_len, n_seg, frame_segment, frame_order, order_offset, state=state)
         return self
 
     def combine(self, group=None):
-        """Merge the ranks' counters: one all-gather of the flat state (tens of KB per rank, latency-bound
-        over NVLink), then SUM of the counters and MIN of the first-seen indices locally.  No-op
-        without an initialised process group."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            world = dist.get_world_size(group)
-            parts = [torch.empty_like(self._flat) for _ in range(world)]
-            dist.all_gather(parts, self._flat, group=group)
-            stacked = torch.stack(parts)
-            self._flat[:self._n_sum] = stacked[:, :self._n_sum].sum(dim=0, dtype=torch.int32)
-            self._flat[self._n_sum:] = stacked[:, self._n_sum:].amin(dim=0)
+        """Merge the ranks' counters (tens of KB per rank, latency-bound over NVLink).  Owned mode: one
+        in-place all-gather of this rank's block.  General mode: one all-gather of the flat state, then SUM
+        of the counters and MIN of the first-seen indices locally.  No-op without a process group."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return self
+        world = dist.get_world_size(group)
+        if self.owned:
+            if world * self.owned[1] != self.n_segments or dist.get_rank(group) != self.owned[0] // self.owned[1]:
+                raise ValueError("owned blocks must follow the rank order of the group")
+            k = self.owned[0] // self.owned[1]
+            mine = self._flat[k * self._block_len:(k + 1) * self._block_len]
+            dist.all_gather_into_tensor(self._flat, mine, group=group)
+            return self
+        parts = [torch.empty_like(self._flat) for _ in range(world)]
+        dist.all_gather(parts, self._flat, group=group)
+        stacked = torch.stack(parts)
+        self._flat[:self._n_sum] = stacked[:, :self._n_sum].sum(dim=0, dtype=torch.int32)
+        self._flat[self._n_sum:] = stacked[:, self._n_sum:].amin(dim=0)
         return self
 
     def result(self):
         """Per segment: (pattern uint8 [L] or None, frequency or None, bit_votes int [L], frames)."""
-        hist = self.hist.cpu().numpy()
-        first = self.first_seen.cpu().numpy()
-        votes = self.bit_votes.cpu().numpy()
-        frames = self.seg_frames.cpu().numpy()
+        bins = 1 << self.payload_len
+        hist = self.hist.cpu().numpy().reshape(self.n_segments, bins)
+        first = self.first_seen.cpu().numpy().reshape(self.n_segments, bins)
+        votes = self.bit_votes.cpu().numpy().reshape(self.n_segments, self.payload_len)
+        frames = self.seg_frames.cpu().numpy().reshape(self.n_segments)
         out = []
         for s in range(self.n_segments):
             if frames[s] == 0:
