@@ -94,6 +94,22 @@ def main():
     report("rgb24 fused embed (in place, 6 B/px)", ms_e, n, 6 * h * w)
     report("rgb24 fused extract (3 B/px)", ms_x, n, 3 * h * w)
 
+    # the same kernels on natural-image statistics: the reference's 1080p fixture crop (tests/golden), tiled to
+    # 1080p with a little per-frame noise.  Chroma blocks of real pictures are mostly well dominated; the smooth
+    # synthetic fields above cross zero in U and V and send most warps through the slow path.
+    crop = np.load(os.path.join(ROOT, "tests", "golden", "frame63_crop.npz"))["bgr"]
+    reps = (-(-h // crop.shape[0]), -(-w // crop.shape[1]), 1)
+    tile = torch.from_numpy(np.tile(crop, reps)[:h, :w].copy()).to(DEV)
+    nat = torch.empty((256, h, w, 3), dtype=torch.uint8, device=DEV)
+    gnat = torch.Generator(device=DEV).manual_seed(9)
+    for f0 in range(0, 256, 32):
+        nat[f0:f0 + 32] = (tile[None].float() + 1.5 * torch.randn((32, h, w, 3), device=DEV, generator=gnat)).round().clamp(0, 255).to(torch.uint8)
+    ms_e = timed(lambda: ops.dwtsvd_embed_rgb8_(nat, wm, ln))
+    ms_x = timed(lambda: ops.dwtsvd_extract_rgb8(nat, payload_len=8))
+    report("rgb24 fused embed, natural image tiled (in place, 6 B/px)", ms_e, 256, 6 * h * w)
+    report("rgb24 fused extract, natural image tiled (3 B/px)", ms_x, 256, 3 * h * w)
+    del nat, tile
+
     def unfused():
         yuv = ops.bgr8_to_yuv32(frames[:128])
         ops.dwtsvd_embed_(yuv, wm, ln, channel=1)

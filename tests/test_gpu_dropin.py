@@ -160,3 +160,25 @@ def test_host_buffer_entry_points_match_device_path():
     pageable = planes.copy()
     ops.dwtsvd_mark_host(pageable, pageable, rows, frame_wm_row=frame_row)
     assert np.array_equal(pageable, dst.numpy())
+
+
+def test_embedder_batched_mode_equals_per_frame_mode(golden_dir):
+    """Embedder(batch_frames=N) (optional extension: one upload / launch / download per N frames) writes the
+    very bytes the reference-shaped per-frame loop writes, in order, including a ragged last batch."""
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.video.embedder import Embedder
+    from offmark_b200.video.memory_io import ArrayReader, ArrayWriter
+    from oracle import synth
+    frames = [synth.random_bgr(64, 96, s) for s in range(7)]
+
+    def run(batch):
+        enc = DwtDctSvdEncoder()
+        enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(frames[0].shape)))
+        w = ArrayWriter()
+        Embedder(ArrayReader([f.copy() for f in frames]), enc, w, batch_frames=batch).start()
+        return w.frames
+    one, many = run(1), run(3)
+    assert len(one) == len(many) == len(frames)
+    for a, b in zip(one, many):
+        assert a.dtype == np.uint8 and np.array_equal(a, b)

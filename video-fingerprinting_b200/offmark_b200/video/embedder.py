@@ -15,23 +15,46 @@ class Embedder:
     frame on the GPU from the uint8 upload to the uint8 download: colour conversion, the frame
     plugin's kernels, conversion back, clip and round-half-even all run there."""
 
-    def __init__(self, frame_reader, frame_embedder, frame_writer, device=None):
+    def __init__(self, frame_reader, frame_embedder, frame_writer, device=None, batch_frames=1):
         self.frame_reader = frame_reader
         self.frame_writer = frame_writer
         self.frame_embedder = frame_embedder
         self.device = device
+        self.batch_frames = max(1, int(batch_frames))      # optional extension: frames per kernel launch
 
     def start(self):
         logger.debug('Entering start()')
+        batched = self.batch_frames > 1 and hasattr(self.frame_embedder, "mark_rgb8")
+        pending = []
         while True:
             in_frame = self.frame_reader.read()
             if in_frame is None:
                 logger.info('End of input stream')
                 break
-            self.frame_writer.write(self.mark_frame(in_frame))
+            if not batched:
+                self.frame_writer.write(self.mark_frame(in_frame))
+                continue
+            pending.append(np.ascontiguousarray(in_frame, dtype=np.uint8))
+            if len(pending) == self.batch_frames:
+                self._flush(pending)
+        if pending:
+            self._flush(pending)
         self.frame_reader.close()
         self.frame_writer.close()
         logger.info('Done')
+
+    def _flush(self, pending):
+        """One upload, one fused kernel launch and one download for the whole batch; frames are written
+        in order, byte-identical to the per-frame path."""
+        dev = device_of(self.device)
+        same = all(f.shape == pending[0].shape for f in pending)
+        groups = [pending] if same else [[f] for f in pending]
+        for group in groups:
+            frames = torch.from_numpy(np.stack(group)).to(dev)
+            marked = self.frame_embedder.mark_rgb8(frames).cpu().numpy()
+            for f in marked:
+                self.frame_writer.write(f)
+        pending.clear()
 
     def mark_frame(self, frame_rgb):
         """uint8 H x W x 3 in, uint8 H x W x 3 out (numpy)."""
