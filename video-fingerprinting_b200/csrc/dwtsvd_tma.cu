@@ -13,20 +13,20 @@
 //     per warp; ncu showed the copy engine saturating on those small boxes at 2.3 TB/s -
 //     profiles/r01_summary.md - which is why the copies are now whole rows or whole strips.)
 //   * Each CTA is persistent and owns a ring of kStages strip buffers in shared memory.  It is warp
-//     specialised: eight consumer warps do the arithmetic, a ninth PRODUCER warp only moves data.
+//     specialised: four consumer warps do the arithmetic, a fifth PRODUCER warp only moves data.
 //     The producer issues the bulk loads for the strips the CTA will need next and arms a "full"
 //     mbarrier with the byte count; consumers wait on its phase, and each consumer warp arrives
-//     on the slot's "empty" mbarrier when it is done, so consumer warps never wait for each other
+//     on the slot's "done" mbarrier when it is finished, so consumer warps never wait for each other
 //     (no CTA-wide barrier in the loop).  HBM latency is hidden by the ring depth, no consumer
 //     spends issue slots on global address arithmetic and the 64 source bytes of a tile never
 //     occupy registers for the length of the SVD.
 //   * Narrow planes (at most 128 tiles per row, e.g. the 960-wide chroma planes of 1080p yuv420p) take
 //     two tile rows per work item, so that both packed lanes of every thread stay busy.
 //   * Consumer thread t owns TWO tiles of the strip, t and t + 128 (narrow planes: tile t of the first
-//     and of the second tile row), and runs the eigen-iteration for
-//     both in packed FP32 (FFMA2/FMUL2/FADD2, svd4x2.cuh): the kernels are issue-bound, and a packed
-//     instruction does the work of two for one issue slot.  It reads its 8x8 bytes from shared memory
-//     (conflict-free: a warp reads 256 contiguous bytes per row).  Embed updates the strip in
+//     and of the second tile row), and runs the eigen-iteration for both in packed FP32
+//     (FFMA2/FMUL2/FADD2, svd4x2.cuh): the kernels were issue-bound, and a packed instruction does the
+//     work of two for one issue slot.  It reads its 8x8 bytes from shared memory (conflict-free: a warp
+//     reads 256 contiguous bytes per row).  Embed updates the strip in
 //     shared memory and writes it back with a bulk store (cp.async.bulk ... bulk_group); a slot
 //     is refilled one iteration after its store was committed
 //     (cp.async.bulk.wait_group.read 1), so loads, math and stores of neighbouring strips
@@ -106,9 +106,6 @@ __device__ __forceinline__ uint2 lds_u2(unsigned addr) {
     uint2 r;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
     return r;
-}
-__device__ __forceinline__ void sts_u2(unsigned addr, uint2 v) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 // predicated store: no branch (and no reconvergence bookkeeping) around the 16 row stores of a tile
 __device__ __forceinline__ void sts_u2_if(bool pred, unsigned addr, uint2 v) {
