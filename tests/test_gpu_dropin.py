@@ -182,3 +182,28 @@ def test_embedder_batched_mode_equals_per_frame_mode(golden_dir):
     assert len(one) == len(many) == len(frames)
     for a, b in zip(one, many):
         assert a.dtype == np.uint8 and np.array_equal(a, b)
+
+
+def test_extractor_batched_mode_equals_per_frame_mode():
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.extract.dwt_dct_svd_decoder import DwtDctSvdDecoder
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.degenerator.de_shuffler import DeShuffler
+    from offmark_b200.video.embedder import Embedder
+    from offmark_b200.video.extractor import Extractor
+    from offmark_b200.video.memory_io import ArrayReader, ArrayWriter
+    from oracle import synth
+    frames = [synth.random_bgr(128, 192, s) for s in range(5)]
+    enc = DwtDctSvdEncoder()
+    enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(frames[0].shape)))
+    w = ArrayWriter()
+    Embedder(ArrayReader(frames), enc, w, batch_frames=4).start()
+
+    def run(batch):
+        ex = Extractor(ArrayReader(w.frames), DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((8,)), batch_frames=batch)
+        ex.start()
+        return ex.patterns
+    one, many = run(1), run(2)
+    assert len(one) == len(many) == len(frames)
+    for a, b in zip(one, many):
+        assert np.array_equal(a, b) and np.array_equal(a, PAYLOAD)

@@ -14,22 +14,58 @@ class Extractor:
     """Same frame loop as the reference (extractor.py:17-28); ``__check_frame`` (:30-34) runs the
     colour conversion, the frame plugin and the per-frame vote on the GPU and logs the pattern."""
 
-    def __init__(self, frame_reader, frame_extractor, degenerator, device=None):
+    def __init__(self, frame_reader, frame_extractor, degenerator, device=None, batch_frames=1):
         self.frame_reader = frame_reader
         self.frame_extractor = frame_extractor
         self.degenerator = degenerator
         self.device = device
+        self.batch_frames = max(1, int(batch_frames))      # optional extension: frames per kernel launch
+        self.patterns = []                                 # optional extension: every pattern that was logged
 
     def start(self):
         logger.debug('Entering start()')
+        batched = (self.batch_frames > 1 and hasattr(self.frame_extractor, "decode_rgb8")
+                   and hasattr(self.degenerator, "degenerate_counts"))
+        pending = []
         while True:
             in_frame = self.frame_reader.read()
             if in_frame is None:
                 logger.info('End of input stream')
                 break
-            logger.info(self.check_frame(in_frame))
+            if not batched:
+                self._log(self.check_frame(in_frame))
+                continue
+            pending.append(np.ascontiguousarray(in_frame, dtype=np.uint8))
+            if len(pending) == self.batch_frames:
+                self._flush(pending)
+        if pending:
+            self._flush(pending)
         self.frame_reader.close()
         logger.info('Done')
+
+    def _log(self, pattern):
+        self.patterns.append(pattern)
+        logger.info(pattern)
+
+    def _flush(self, pending):
+        """One upload, one fused extract launch and one vote launch for the whole batch; the patterns are
+        logged in frame order and equal the per-frame path's."""
+        dev = device_of(self.device)
+        same = all(f.shape == pending[0].shape for f in pending)
+        for group in ([pending] if same else [[f] for f in pending]):
+            frames = torch.from_numpy(np.stack(group)).to(dev)
+            h, w = frames.shape[1], frames.shape[2]
+            scale = self.frame_extractor.scales[1]
+            length = self.degenerator.payload_len
+            if scale <= 0:
+                for f in group:
+                    self._log(self.check_frame(f))
+                continue
+            raw, counts = ops.dwtsvd_extract_rgb8(frames, scale=scale, channel=1, payload_len=length)
+            patterns, _ = self.degenerator.degenerate_counts(counts, h * w // 64)
+            for p in patterns.cpu().numpy():
+                self._log(p)
+        pending.clear()
 
     def check_frame(self, frame_rgb):
         dev = device_of(self.device)
