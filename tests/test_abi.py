@@ -75,3 +75,34 @@ def test_pack_unpack_bits_roundtrip():
             assert (words[1, c >> 5] >> (c & 31)) & 1 == bits[1, c]
     with pytest.raises(ValueError):
         ops.pack_bits(np.array([0, 2, 1]))
+
+
+def _build_c_demo(tmp_path):
+    import shutil
+    import subprocess
+    from b200wm import _lib
+    gcc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if not gcc or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA headers are not available")
+    exe = str(tmp_path / "c_abi_demo")
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe, "-L" + lib_dir, "-lb200wm",
+           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + lib_dir]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    return exe
+
+
+def test_plain_c_caller_compiles_and_links(tmp_path):
+    """The boundary is usable from C with nothing but include/b200wm.h and the shared library."""
+    assert os.path.exists(_build_c_demo(tmp_path))
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_recovers_the_payload(tmp_path):
+    import subprocess
+    proc = subprocess.run([_build_c_demo(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert "recovered payload: 0 1 1 0 0 1 0 1" in proc.stdout and "matches" in proc.stdout
