@@ -409,3 +409,22 @@ def test_i420_native_planes(which):
         got = out[f, lo:lo + ph * pw].reshape(ph, pw)
         assert np.abs(got.astype(np.int16) - want)[ok].max() <= 1        # tolerance: 1 LSB (north_star)
         _assert_bits_match(ops.unpack_bits(raw[f:f + 1], ph * pw // 64), o_svd.extract_plane(got), got.astype(np.float32), f"i420 {which}")
+
+
+def test_new_entry_points_reject_bad_arguments():
+    """Status codes of the copies / resize entry points map to the exceptions of b200wm._lib.check."""
+    from b200wm import ops
+    DEV = _dev()
+    planes = torch.zeros((2, 64, 512), dtype=torch.uint8, device=DEV)
+    packed, n = ops.pack_bits(np.zeros((2, 64 * 512 // 64), dtype=np.int64), device=DEV)
+    with pytest.raises(ValueError):                      # more copies than watermark rows and no row table
+        ops.dwtsvd_embed_copies(planes, packed, n, 3)
+    with pytest.raises(ValueError):                      # float planes: the multi-copy kernel is uint8 only
+        ops.dwtsvd_embed_copies(planes.float(), packed, n, 2)
+    with pytest.raises(ValueError):                      # row table of the wrong shape
+        ops.dwtsvd_embed_copies(planes, packed, n, 2, copy_wm_row=torch.zeros((2, 3), dtype=torch.int32, device=DEV))
+    assert ops.dwtsvd_embed_copies(planes, packed, n, 0).shape[0] == 0          # zero copies: nothing to do
+    empty = ops.attack_resize(planes[:0], (256, 32), ops.INTER_AREA)            # zero frames: nothing to do
+    assert empty.shape == (0, 32, 256)
+    with pytest.raises(ValueError):
+        ops.i420_plane(torch.zeros((2, 100), dtype=torch.uint8, device=DEV), 64, 512)

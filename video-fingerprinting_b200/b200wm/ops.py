@@ -180,6 +180,8 @@ def dwtsvd_embed_copies(planes, wm_packed, wm_len, n_copies, scale=15.0, copy_wm
     if copy_wm_row is not None and (copy_wm_row.dtype != torch.int32 or tuple(copy_wm_row.shape) != (pl.n_frames, n_copies)
                                     or not copy_wm_row.is_cuda or not copy_wm_row.is_contiguous()):
         raise ValueError("copy_wm_row must be a contiguous CUDA int32 [n_frames, n_copies] tensor")
+    if n_copies == 0:
+        return out
     check(lib.b200wm_dwtsvd_embed_copies(_ptr(v), C.byref(pl), _ptr(out), int(out.stride(0)) if n_copies else 0, n_copies,
                                          _ptr(wm_packed), wm_packed.shape[0], wm_packed.shape[1], int(wm_len),
                                          _ptr(copy_wm_row), float(scale), _stream()))
