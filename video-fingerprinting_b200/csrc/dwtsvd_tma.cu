@@ -222,14 +222,14 @@ template <bool kNarrow>
 struct TilePair {
     bool live_lo, live_hi, warp_live_lo, warp_live_hi;
     unsigned off_lo, off_hi, hi_delta;
-    __device__ __forceinline__ TilePair(int t, const Item& it, const StripGeom& sg) {
+    __device__ __forceinline__ TilePair(int t, const Item& it, const StripGeom& sg, unsigned slot_pitch) {
         live_lo = t < it.tiles;
         warp_live_lo = (t & ~31) < it.tiles;
         if (kNarrow) {
             live_hi = live_lo && it.rows == 2;
             warp_live_hi = warp_live_lo && it.rows == 2;
             hi_delta = (unsigned)sg.g.tiles_x;
-            off_hi = live_hi ? 8u * sg.slot_pitch + (unsigned)t * 8u : 0u;
+            off_hi = live_hi ? 8u * slot_pitch + (unsigned)t * 8u : 0u;
         } else {
             live_hi = t + kStripThreads < it.tiles;
             warp_live_hi = ((t + kStripThreads) & ~31) < it.tiles;
@@ -242,7 +242,9 @@ struct TilePair {
 
 // ---- extract -------------------------------------------------------------------------------------------
 // raw_bits must be zero on entry (the launcher clears it): warps OR their bits in.
-template <bool kWhole, bool kNarrow>
+// kPitch: the shared-memory row pitch when it is known at compile time (1920 for 1080p strips and 4K chunks,
+// 960 for the chroma planes of 1080p yuv420p), 0 otherwise: row offsets then fold into the LDS / STS immediates.
+template <bool kWhole, bool kNarrow, unsigned kPitch>
 __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src,
                                                                                                ExtractArgs ex, StripGeom sg) {
     constexpr int kStages = kExtractStages;
@@ -288,7 +290,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
         const Item it = item_of<kWhole, kNarrow>(i, sg);
         const unsigned slot = ring + stage * sg.slot_bytes;
-        const TilePair<kNarrow> tp(t, it, sg);
+        const unsigned sp = kPitch ? kPitch : sg.slot_pitch;
+        const TilePair<kNarrow> tp(t, it, sg, sp);
         mbar_wait(full0 + 8 * stage, parity);
         unsigned bits;
         {
@@ -297,8 +300,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
                 uint2 ra[8], rb[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    ra[r] = lds_u2(slot + r * sg.slot_pitch + tp.off_lo);
-                    rb[r] = lds_u2(slot + r * sg.slot_pitch + tp.off_hi);
+                    ra[r] = lds_u2(slot + tp.off_lo + r * sp);
+                    rb[r] = lds_u2(slot + tp.off_hi + r * sp);
                 }
                 sums_from_rows_x2(ra, rb, S);
             }
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
 }
 
 // ---- embed ----------------------------------------------------------------------------------------------
-template <bool kWhole, bool kNarrow>
+template <bool kWhole, bool kNarrow, unsigned kPitch>
 __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                       EmbedArgs em, StripGeom sg) {
     constexpr int kStages = kEmbedStages;
@@ -384,7 +387,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
         const Item it = item_of<kWhole, kNarrow>(i, sg);
         const unsigned slot = ring + stage * sg.slot_bytes;
-        const TilePair<kNarrow> tp(t, it, sg);
+        const unsigned sp = kPitch ? kPitch : sg.slot_pitch;
+        const TilePair<kNarrow> tp(t, it, sg, sp);
         // the watermark bits of this warp's tiles (32 per half), funnel-shifted out of the packed row;
         // issued before the wait so that their latency hides behind it
         const int row = em.frame_row ? em.frame_row[it.frame] : 0;
@@ -412,8 +416,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
                     uint2 ra[8], rb[8];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        ra[r] = lds_u2(mine_lo + r * sg.slot_pitch);
-                        rb[r] = lds_u2(mine_hi + r * sg.slot_pitch);
+                        ra[r] = lds_u2(mine_lo + r * sp);
+                        rb[r] = lds_u2(mine_hi + r * sp);
                     }
                     sums_from_rows_x2(ra, rb, S);
                 }
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
                 const unsigned b23 = __byte_perm(__float_as_uint(D[4 * i2 + 2].y), __float_as_uint(D[4 * i2 + 3].y), 0x5410);
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const unsigned ro = (2 * i2 + rr) * sg.slot_pitch;
+                    const unsigned ro = (2 * i2 + rr) * sp;
                     sts_u2_if(tp.live_lo, mine_lo + ro, add_clamp_row(lds_u2(mine_lo + ro), a01, a23));
                     sts_u2_if(tp.live_hi, mine_hi + ro, add_clamp_row(lds_u2(mine_hi + ro), b01, b23));
                 }
@@ -494,26 +498,26 @@ static StripGeom make_strip_geom(const TileGeom& g, const b200wm_plane* pl) {
     return sg;
 }
 
-template <bool kWhole, bool kNarrow>
+template <bool kWhole, bool kNarrow, unsigned kPitch>
 static int launch_extract_t(const uint8_t* src, const ExtractArgs& xa, const StripGeom& sg, cudaStream_t stream) {
     const size_t smem = (size_t)kExtractStages * sg.slot_bytes;
     int blocks = 0;
-    const int rc = persistent_grid(dwtsvd_extract_tma_kernel<kWhole, kNarrow>, smem, &blocks);
+    const int rc = persistent_grid(dwtsvd_extract_tma_kernel<kWhole, kNarrow, kPitch>, smem, &blocks);
     if (rc) return rc;
     if (sg.total < blocks) blocks = sg.total;
-    dwtsvd_extract_tma_kernel<kWhole, kNarrow><<<blocks, kCtaThreads, smem, stream>>>(src, xa, sg);
+    dwtsvd_extract_tma_kernel<kWhole, kNarrow, kPitch><<<blocks, kCtaThreads, smem, stream>>>(src, xa, sg);
     B200WM_LAUNCH_CHECK("dwtsvd_extract_tma_kernel");
     return B200WM_OK;
 }
 
-template <bool kWhole, bool kNarrow>
+template <bool kWhole, bool kNarrow, unsigned kPitch>
 static int launch_embed_t(const uint8_t* src, uint8_t* dst, const EmbedArgs& ea, const StripGeom& sg, cudaStream_t stream) {
     const size_t smem = (size_t)kEmbedStages * sg.slot_bytes;
     int blocks = 0;
-    const int rc = persistent_grid(dwtsvd_embed_tma_kernel<kWhole, kNarrow>, smem, &blocks);
+    const int rc = persistent_grid(dwtsvd_embed_tma_kernel<kWhole, kNarrow, kPitch>, smem, &blocks);
     if (rc) return rc;
     if (sg.total < blocks) blocks = sg.total;
-    dwtsvd_embed_tma_kernel<kWhole, kNarrow><<<blocks, kCtaThreads, smem, stream>>>(src, dst, ea, sg);
+    dwtsvd_embed_tma_kernel<kWhole, kNarrow, kPitch><<<blocks, kCtaThreads, smem, stream>>>(src, dst, ea, sg);
     B200WM_LAUNCH_CHECK("dwtsvd_embed_tma_kernel");
     return B200WM_OK;
 }
@@ -521,8 +525,12 @@ static int launch_embed_t(const uint8_t* src, uint8_t* dst, const EmbedArgs& ea,
 int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const TileGeom& g, ExtractArgs xa, cudaStream_t stream) {
     const StripGeom sg = make_strip_geom(g, pl);
     const uint8_t* p = (const uint8_t*)src;
-    if (sg.narrow) return sg.whole ? launch_extract_t<true, true>(p, xa, sg, stream) : launch_extract_t<false, true>(p, xa, sg, stream);
-    return sg.whole ? launch_extract_t<true, false>(p, xa, sg, stream) : launch_extract_t<false, false>(p, xa, sg, stream);
+    if (sg.narrow) {
+        if (sg.whole) return sg.slot_pitch == 960 ? launch_extract_t<true, true, 960>(p, xa, sg, stream) : launch_extract_t<true, true, 0>(p, xa, sg, stream);
+        return launch_extract_t<false, true, 0>(p, xa, sg, stream);
+    }
+    if (sg.whole) return sg.slot_pitch == 1920 ? launch_extract_t<true, false, 1920>(p, xa, sg, stream) : launch_extract_t<true, false, 0>(p, xa, sg, stream);
+    return sg.slot_pitch == 1920 ? launch_extract_t<false, false, 1920>(p, xa, sg, stream) : launch_extract_t<false, false, 0>(p, xa, sg, stream);
 }
 
 int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, const TileGeom& g, EmbedArgs ea,
@@ -530,8 +538,12 @@ int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, 
     const StripGeom sg = make_strip_geom(g, pl);
     const uint8_t* p = (const uint8_t*)src;
     uint8_t* d = (uint8_t*)dst;
-    if (sg.narrow) return sg.whole ? launch_embed_t<true, true>(p, d, ea, sg, stream) : launch_embed_t<false, true>(p, d, ea, sg, stream);
-    return sg.whole ? launch_embed_t<true, false>(p, d, ea, sg, stream) : launch_embed_t<false, false>(p, d, ea, sg, stream);
+    if (sg.narrow) {
+        if (sg.whole) return sg.slot_pitch == 960 ? launch_embed_t<true, true, 960>(p, d, ea, sg, stream) : launch_embed_t<true, true, 0>(p, d, ea, sg, stream);
+        return launch_embed_t<false, true, 0>(p, d, ea, sg, stream);
+    }
+    if (sg.whole) return sg.slot_pitch == 1920 ? launch_embed_t<true, false, 1920>(p, d, ea, sg, stream) : launch_embed_t<true, false, 0>(p, d, ea, sg, stream);
+    return sg.slot_pitch == 1920 ? launch_embed_t<false, false, 1920>(p, d, ea, sg, stream) : launch_embed_t<false, false, 0>(p, d, ea, sg, stream);
 }
 
 }  // namespace b200wm
