@@ -207,3 +207,34 @@ def test_extractor_batched_mode_equals_per_frame_mode():
     assert len(one) == len(many) == len(frames)
     for a, b in zip(one, many):
         assert np.array_equal(a, b) and np.array_equal(a, PAYLOAD)
+
+
+def test_fingerprint_layer_copy_sequence_roundtrip():
+    """tests/mark_video_to_hls.py + tests/detect_watermarks.py on the GPU: N marked copies per segment from one
+    read, a player picks one copy per segment, detection recovers the copy sequence - with the payload map
+    and, without it, by decoding the pattern; payload scheme and JSON shapes as in the reference."""
+    from offmark_b200 import fingerprint as fp
+    from oracle import synth
+    dev = torch.device("cuda:0")
+    n_seg, per, n_copies, h, w = 4, 6, 3, 240, 320
+    seg_numbers = [0, 1, 2, 17]                     # 17 % 16 == 1: the 4-bit scheme wraps (mark_video_to_hls.py:38)
+    frame_seg = [seg_numbers[f // per] for f in range(n_seg * per)]
+    planes = torch.from_numpy(np.stack([synth.luma_plane_u8(h, w, f, 77) for f in range(n_seg * per)])).to(dev)
+    copies, payloads, seg_copies = fp.mark_segment_copies(planes, frame_seg, n_copies)
+    assert copies.shape == (n_copies, n_seg * per, h, w)
+    assert payloads["2_1"] == o_pay.payload_for_segment_copy(2, 1).tolist() == [0, 0, 1, 0, 0, 0, 0, 1]
+    assert seg_copies["17"][2] == {"file": "marked_seg17_copy2.mp4", "payload": o_pay.payload_for_segment_copy(17, 2).tolist(), "copy_index": 2}
+    assert np.array_equal(fp.generate_payload_for_segment(300), o_pay.payload_for_segment(300))
+    chosen = [2, 0, 1, 2]                           # the copy this player received for each segment
+    stream = torch.cat([copies[chosen[i], i * per:(i + 1) * per] for i in range(n_seg)])
+    with_map = fp.detect_segment_copies(stream, frame_seg, segment_payloads=payloads)
+    assert [r["detected_copy_index"] for r in with_map] == [2, 0, 1, 2]
+    assert all(r["success"] and r["match_frequency"] == 1.0 for r in with_map)
+    assert fp.copy_fingerprint(with_map) == ([2, 0, 1, 2], "2012")
+    without = fp.detect_segment_copies(stream, frame_seg)
+    assert [r["detected_copy_index"] for r in without] == [2, 0, 1, 2]
+    assert fp.decode_watermark_pattern(o_pay.payload_for_segment_copy(5, 9)) == o_pay.segment_copy_from_pattern(o_pay.payload_for_segment_copy(5, 9)) == (5, 9)
+    # a payload map that does not list the received copies identifies nothing (detect_watermarks.py:339-347)
+    other = {k: v for k, v in payloads.items() if k.endswith("_1")}
+    partial = fp.detect_segment_copies(stream, frame_seg, segment_payloads=other)
+    assert [r["detected_copy_index"] for r in partial] == [None, None, 1, None]
