@@ -152,6 +152,13 @@ B200WM_API int b200wm_dwtsvd_extract(const void* src, const b200wm_plane* plane,
 
 /* Debug/validation: sigma_0 of every walked block as float32 [n_frames, tile_count]. */
 B200WM_API int b200wm_dwtsvd_sigma(const void* src, const b200wm_plane* plane, float* sigma, void* stream);
+/*
+ * The same quantity computed as the reference writes it, svd(cv2.dct(block)).s[0]
+ * (extract/dwt_dct_svd_decoder.py:35), with orthonormal 4-point DCT-II butterflies on the LL block.
+ * The production kernels drop the DCT (it is orthogonal, sigma is invariant); this entry point exists
+ * so that tests can check that claim on the device.  Same output as b200wm_dwtsvd_sigma.
+ */
+B200WM_API int b200wm_dwtsvd_sigma_dct(const void* src, const b200wm_plane* plane, float* sigma, void* stream);
 
 /* ---- 8x8 block-DCT quantisation-index pair --------------------------------------- */
 /*

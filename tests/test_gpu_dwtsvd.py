@@ -93,6 +93,24 @@ def test_sigma_matches_float64_truth():
         np.testing.assert_allclose(sig, s64, rtol=3e-7, atol=1e-6)
 
 
+def test_block_dct_is_dropped_without_changing_sigma():
+    """The production kernels skip the reference's 4x4 block DCT (svd(cv2.dct(block)),
+    dwt_dct_svd_decoder.py:35) because it is orthogonal.  b200wm_dwtsvd_sigma_dct keeps it (4-point
+    butterflies): both agree with each other and with the float64 truth of the reference's expression."""
+    from b200wm import ops
+    for plane in (synth.luma_plane_u8(240, 320, 0, 1), synth.full_range_plane_u8(128, 128, 2)):
+        yuv = np.zeros(plane.shape + (3,), dtype=np.float32)
+        yuv[:, :, 1] = plane
+        _, s64 = o_svd.decode_sigma(yuv)
+        t = torch.from_numpy(plane).to(_dev())
+        fast = ops.dwtsvd_sigma(t)[0].cpu().numpy()
+        faithful = ops.dwtsvd_sigma_dct(t)[0].cpu().numpy()
+        np.testing.assert_allclose(faithful, s64, rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(faithful, fast, rtol=1e-6, atol=1e-5)
+        tf = torch.from_numpy(yuv).to(_dev())
+        np.testing.assert_allclose(ops.dwtsvd_sigma_dct(tf, channel=1)[0].cpu().numpy(), s64, rtol=1e-6, atol=1e-5)
+
+
 @pytest.mark.parametrize("h,w", [(1080, 1920), (240, 320), (37, 53), (100, 132), (8, 8)])
 def test_embed_u8_planes_within_1_lsb_of_oracle(h, w):
     from b200wm import ops

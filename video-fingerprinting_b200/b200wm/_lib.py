@@ -41,6 +41,7 @@ PROTOTYPES = {
     "b200wm_dwtsvd_embed_copies": (C.c_int, [_vp, _PP, _vp, _i64, _i32, _vp, _i32, _i32, _i64, _vp, _f32, _vp]),
     "b200wm_dwtsvd_extract": (C.c_int, [_vp, _PP, _f32, _vp, _i32, _i32, _vp, _vp]),
     "b200wm_dwtsvd_sigma": (C.c_int, [_vp, _PP, _vp, _vp]),
+    "b200wm_dwtsvd_sigma_dct": (C.c_int, [_vp, _PP, _vp, _vp]),
     "b200wm_dct8_masks": (C.c_int, [_vp, _PP, _vp, _vp, _vp, _vp]),
     "b200wm_dct8_embed": (C.c_int, [_vp, _vp, _PP, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _f32, _vp]),
     "b200wm_dct8_extract": (C.c_int, [_vp, _PP, _vp, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp]),

@@ -212,6 +212,16 @@ def dwtsvd_sigma(planes, channel=None):
     return sigma
 
 
+def dwtsvd_sigma_dct(planes, channel=None):
+    """sigma_0 computed WITH the 4x4 block DCT, as the reference writes it (validation aid)."""
+    require_cuda()
+    v, pl = describe(planes, channel)
+    _, tiles, _ = geometry(pl.height, pl.width)
+    sigma = _empty((pl.n_frames, tiles), torch.float32, v.device)
+    check(lib.b200wm_dwtsvd_sigma_dct(_ptr(v), C.byref(pl), _ptr(sigma), _stream()))
+    return sigma
+
+
 # ----------------------------------------------------------------------------- 8x8 DCT pair
 def dct8_masks(lum, channel=None):
     """-> (block_mean f32 [N, nb], tex_mask f32 [N, nb], frame_sum f64 [N])."""

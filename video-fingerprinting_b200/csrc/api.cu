@@ -38,6 +38,7 @@ int launch_extract_rgb8(const uint8_t*, int, int, int, long long, long long, int
 int mark_host(const uint8_t*, uint8_t*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float, int);
 int detect_host(const uint8_t*, const b200wm_plane*, float, int, const int32_t*, uint8_t*, uint32_t*, int32_t*, int);
 int host_scratch_release();
+int launch_dwtsvd_sigma_dct(const void*, const b200wm_plane*, float*, cudaStream_t);
 void set_path(int);
 int get_path();
 int launch_yuv32_to_bgr8(const float*, uint8_t*, long long, cudaStream_t);
@@ -109,6 +110,10 @@ B200WM_API int b200wm_dwtsvd_extract(const void* src, const b200wm_plane* plane,
                           int32_t words_per_frame, int32_t payload_len, int32_t* pos_counts, void* stream) {
     return launch_dwtsvd_extract(src, plane, scale, raw_bits, words_per_frame, payload_len, pos_counts, nullptr,
                                  (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_dwtsvd_sigma_dct(const void* src, const b200wm_plane* plane, float* sigma, void* stream) {
+    return launch_dwtsvd_sigma_dct(src, plane, sigma, (cudaStream_t)stream);
 }
 
 B200WM_API int b200wm_dwtsvd_sigma(const void* src, const b200wm_plane* plane, float* sigma, void* stream) {

@@ -134,6 +134,40 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_extract_kernel(PlaneArgs pl, 
     }
 }
 
+// Validation kernel: sigma_0 computed the way the reference writes it, WITH the 4x4 DCT
+// (svd(cv2.dct(block)), extract/dwt_dct_svd_decoder.py:35): orthonormal 4-point DCT-II butterflies on the
+// rows and columns of the LL block, then the same top-singular routine.  The production kernels drop
+// the DCT because it is orthogonal (sigma is invariant); tests compare the two on the GPU.
+__device__ __forceinline__ void dct4_1d(float& x0, float& x1, float& x2, float& x3) {
+    const float s0 = x0 + x3, s1 = x1 + x2, d0 = x0 - x3, d1 = x1 - x2;
+    x0 = (s0 + s1) * 0.5f;
+    x2 = (s0 - s1) * 0.5f;
+    x1 = fmaf(d0, 0.65328148243818826f, d1 * 0.27059805007309849f);       // cos(pi/8)/sqrt(2), cos(3pi/8)/sqrt(2)
+    x3 = fmaf(d0, 0.27059805007309849f, d1 * -0.65328148243818826f);
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kThreads) dwtsvd_sigma_dct_kernel(PlaneArgs pl, TileGeom g, float* __restrict__ sigma, int frame0) {
+    const int frame = frame0 + blockIdx.y;
+    const unsigned c = blockIdx.x * kThreads + threadIdx.x;
+    if (c >= (unsigned)g.n_tiles) return;
+    const unsigned ty = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
+    const unsigned tx = c - ty * g.tiles_x;
+    const long long off = frame * pl.frame_stride + (unsigned long long)(ty * 8) * pl.pitch;
+    float B[16];
+    if (kMode == 2) load_tile_generic<float>(pl.src + off + (long long)tx * 8 * pl.elem_stride * 4, pl.pitch, pl.elem_stride, B);
+    else load_tile_generic<uint8_t>(pl.src + off + (long long)tx * 8 * pl.elem_stride, pl.pitch, pl.elem_stride, B);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) B[k] *= 0.5f;                              // Haar LL = 2x2 sum / 2
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dct4_1d(B[4 * i], B[4 * i + 1], B[4 * i + 2], B[4 * i + 3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dct4_1d(B[j], B[4 + j], B[8 + j], B[12 + j]);
+    float v[4];
+    bool zero;
+    sigma[(long long)frame * g.n_tiles + c] = top_singular<false>(B, v, zero);
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
@@ -186,6 +220,24 @@ int launch_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* pl, cons
         else if (mode == 1) dwtsvd_embed_kernel<1><<<grid, kThreads, 0, stream>>>(pa, ea, g, f0);
         else dwtsvd_embed_kernel<2><<<grid, kThreads, 0, stream>>>(pa, ea, g, f0);
         B200WM_LAUNCH_CHECK("dwtsvd_embed_kernel");
+    }
+    return B200WM_OK;
+}
+
+int launch_dwtsvd_sigma_dct(const void* src, const b200wm_plane* pl, float* sigma, cudaStream_t stream) {
+    int rc = validate_plane(pl);
+    if (rc) return rc;
+    if (!src || !sigma) return B200WM_ERR_INVALID;
+    const TileGeom g = make_geom(pl->height, pl->width);
+    if (g.n_tiles == 0 || pl->n_frames == 0) return B200WM_OK;
+    if ((uintptr_t)src % 4 && pl->dtype == B200WM_F32) return B200WM_ERR_INVALID;
+    PlaneArgs pa{(const uint8_t*)src, nullptr, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
+    const unsigned gx = (g.n_tiles + kThreads - 1) / kThreads;
+    for (int f0 = 0; f0 < pl->n_frames; f0 += 65535) {
+        const dim3 grid(gx, (unsigned)((pl->n_frames - f0) < 65535 ? (pl->n_frames - f0) : 65535));
+        if (pl->dtype == B200WM_F32) dwtsvd_sigma_dct_kernel<2><<<grid, kThreads, 0, stream>>>(pa, g, sigma, f0);
+        else dwtsvd_sigma_dct_kernel<1><<<grid, kThreads, 0, stream>>>(pa, g, sigma, f0);
+        B200WM_LAUNCH_CHECK("dwtsvd_sigma_dct_kernel");
     }
     return B200WM_OK;
 }
