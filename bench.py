@@ -54,6 +54,8 @@ def parse_args():
     p.add_argument("--cpu-frames-per-core", type=int, default=8)     # ~2 s per frame and core: 10-20 s of CPU work
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--size", default="1080p", choices=["1080p", "4k"],
+                   help="1080p: BASELINE configs[1] (the headline); 4k: configs[2], 3840x2160 planes (750 frames per GPU by default)")
     p.add_argument("--path", type=int, default=0, choices=[0, 1],
                    help="0: TMA-staged persistent kernels (default), 1: vectorised-load kernels (A/B evidence)")
     return p.parse_args()
@@ -291,6 +293,11 @@ def run_reference(args):
 
 
 def workload_config(args, frames_per_gpu):
+    if H != 1080:
+        return {"workload": "4K (3840x2160) YUV420 synthetic frames sharded across the GPUs, DwtDctSvd embed + extract + vote on the Y plane",
+                "frames_per_gpu": frames_per_gpu, "height": H, "width": W, "io_dtype": "u8", "layout": "planar I420 in HBM",
+                "payload_bits": PAYLOAD_LEN, "segment_frames": SEGMENT_FRAMES, "scale": 15, "blk": 4,
+                "cache": "inputs larger than L2 (6.2 GB of Y planes per pass vs 126 MB L2)"}
     return {"workload": "1080p30 YUV420 synthetic batch, DwtDctSvd embed + extract + vote on the Y plane",
             "frames_per_gpu": frames_per_gpu, "height": H, "width": W, "io_dtype": "u8", "layout": "planar I420 in HBM",
             "payload_bits": PAYLOAD_LEN, "segment_frames": SEGMENT_FRAMES, "scale": 15, "blk": 4,
@@ -299,7 +306,16 @@ def workload_config(args, frames_per_gpu):
 
 # --------------------------------------------------------------------------------- B200 arm
 def main():
+    global H, W, FRAME_BYTES_I420, METRIC
     args = parse_args()
+    if args.size == "4k":                 # BASELINE configs[2]; the headline line stays the 1080p one
+        H, W = 2160, 3840
+        FRAME_BYTES_I420 = W * H * 3 // 2
+        METRIC = "frames_per_sec_4k_embed_extract"
+        if args.frames == 3000:
+            args.frames = 750
+        args.e2e_frames = min(args.e2e_frames, args.frames)
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         return run_reference(args)
 
@@ -416,7 +432,7 @@ def main():
     # launch size (profiles/r01_traffic.json); null when the workload differs from the captured one
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and n_frames == 3000:
+    if os.path.exists(tpath) and n_frames == 3000 and H == 1080:
         with open(tpath) as f:
             cap = json.load(f)["kernels"].get(dominant)
         if cap and cap.get("frames") == n_frames:
