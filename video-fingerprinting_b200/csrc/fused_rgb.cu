@@ -27,10 +27,6 @@ __device__ __forceinline__ void px_to_yuv(float c0, float c1, float c2, float& y
     v = fmaf(c2 - y, 0.877f, 0.5f);
 }
 
-__device__ __forceinline__ unsigned sat_u8(float f) {
-    return (unsigned)__float2int_rn(fminf(fmaxf(f, 0.0f), 255.0f));
-}
-
 // bytes of one tile row: 8 pixels x 3 channels = 24 bytes = 6 words
 template <bool kAligned>
 __device__ __forceinline__ void load_row24(const uint8_t* p, unsigned (&w)[6]) {
@@ -46,7 +42,21 @@ __device__ __forceinline__ void load_row24(const uint8_t* p, unsigned (&w)[6]) {
 }
 
 __device__ __forceinline__ float byte_of(const unsigned (&w)[6], int i) {
-    return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+    return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);       // compiles to one I2F with a byte selector
+}
+
+// 24 colour values of a row -> 24 bytes: clip(., 0, 255) then round-half-even (video/embedder.py:37-38) equals
+// round-half-even then clamp; adding 1.5 * 2^23 rounds and leaves the integer in the low mantissa bits, which
+// are packed as int16 lanes, clamped by one DPX instruction per two values and narrowed to bytes.
+__device__ __forceinline__ void pack_row24(const float (&c)[24], unsigned (&out)[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const unsigned b0 = __float_as_uint(c[4 * k] + 12582912.0f), b1 = __float_as_uint(c[4 * k + 1] + 12582912.0f);
+        const unsigned b2 = __float_as_uint(c[4 * k + 2] + 12582912.0f), b3 = __float_as_uint(c[4 * k + 3] + 12582912.0f);
+        const unsigned e = __viaddmin_s16x2_relu(__byte_perm(b0, b2, 0x5410), 0u, 0x00FF00FFu);
+        const unsigned o = __viaddmin_s16x2_relu(__byte_perm(b1, b3, 0x5410), 0u, 0x00FF00FFu);
+        out[k] = __byte_perm(e, o, 0x6240);
+    }
 }
 
 // kMask: bit c set = YUV channel c is marked (scale[c] > 0); compile-time so that unmarked channels
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(128, 4) dwtsvd_embed_rgb8_kernel(RgbArgs a, Em
     for (int r = 0; r < 8; ++r) {
         unsigned raw[6];
         load_row24<kAligned>(a.src + off + (unsigned long long)r * a.pitch, raw);
-        unsigned out[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        float cv[24];
 #pragma unroll
         for (int px = 0; px < 8; ++px) {
             float y, u, v;
@@ -104,14 +114,12 @@ __global__ void __launch_bounds__(128, 4) dwtsvd_embed_rgb8_kernel(RgbArgs a, Em
             if (kMask & 2) u += D[1][k];
             if (kMask & 4) v += D[2][k];
             const float du = u - 0.5f, dv = v - 0.5f;
-            const float c0 = fmaf(du, 2.032f, y);
-            const float c1 = fmaf(dv, -0.581f, fmaf(du, -0.395f, y));
-            const float c2 = fmaf(dv, 1.14f, y);
-            const int b0 = 3 * px;
-            out[b0 >> 2] |= sat_u8(c0) << (8 * (b0 & 3));
-            out[(b0 + 1) >> 2] |= sat_u8(c1) << (8 * ((b0 + 1) & 3));
-            out[(b0 + 2) >> 2] |= sat_u8(c2) << (8 * ((b0 + 2) & 3));
+            cv[3 * px] = fmaf(du, 2.032f, y);
+            cv[3 * px + 1] = fmaf(dv, -0.581f, fmaf(du, -0.395f, y));
+            cv[3 * px + 2] = fmaf(dv, 1.14f, y);
         }
+        unsigned out[6];
+        pack_row24(cv, out);
         uint8_t* o = a.dst + off + (unsigned long long)r * a.pitch;
         if (kAligned) {
             uint2* q = reinterpret_cast<uint2*>(o);
