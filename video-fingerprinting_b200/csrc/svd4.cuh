@@ -194,6 +194,7 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
         float H[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) H[k] = G[k];
+        float lam_prev = -1.0f;
 #pragma unroll 1
         for (int round = 0; round < kSquarings && !done; ++round) {
             square_sym4(H);
@@ -205,6 +206,12 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
             for (int k = 0; k < 4; ++k) x[k] *= up2;
             symv4(G, x, w);
             done = rayleigh_check(x, w, tr, xw, xx);
+            // A block that is not dominated (2 lambda_0 <= tr G: noise-like content, flat chroma) can never be
+            // certified.  Once its Rayleigh quotient has stopped moving while 2 lambda <= tr there is no point in
+            // squaring further: leave for the direct solver now instead of after all kSquarings rounds.
+            const float lam = xw / xx;
+            if (!done && 2.0f * lam <= tr && fabsf(lam - lam_prev) <= 1e-6f * lam) break;
+            lam_prev = lam;
         }
     }
     if (done) {
