@@ -67,6 +67,18 @@ def main():
         report(f"4K embed+extract ({tag})", ms_e + ms_x, n, 3 * h * w)
     ops.set_path(0)
     del src, dst
+    # ---- portrait 1080 x 1920 luma (135 tiles per row, rows only 8-byte aligned: whole-strip bulk copies still apply)
+    hp, wp, n = 1920, 1080, 1024
+    src = planes(n, hp, wp)
+    dst = src.clone()
+    wmp, lnp = ops.pack_bits(Shuffler(key=0).generate_wm(payload, (1, hp * wp // 64))[0], device=DEV)
+    for path, tag in ((0, "tma"), (1, "ldg")):
+        ops.set_path(path)
+        ms_e = timed(lambda: ops.dwtsvd_embed_(src, wmp, lnp, out=dst))
+        ms_x = timed(lambda: ops.dwtsvd_extract(dst, payload_len=8))
+        report(f"portrait 1080x1920 embed+extract ({tag})", ms_e + ms_x, n, 3 * hp * wp)
+    ops.set_path(0)
+    del src, dst
     # ---- chroma plane of yuv420p 1080p frames, marked in place through a strided view
     h, w, n = 1080, 1920, 1024
     frames = torch.empty((n, h * w * 3 // 2), dtype=torch.uint8, device=DEV)

@@ -313,8 +313,8 @@ def test_random_geometries_both_paths_agree():
     planes and bits."""
     from b200wm import ops
     rng = np.random.RandomState(12345)
-    widths = [64, 320, 528, 784, 1024, 1040, 1936, 2048, 2064, 3840, 4112, 6160]   # <= 128 tiles: two tile rows per item; 258, 480, 514, 770 tiles: 2, 2, 3, 4 chunks
-    for case in range(24):
+    widths = [64, 320, 528, 784, 1000, 1024, 1040, 1080, 1936, 2048, 2064, 3840, 4112, 6160]   # <= 128 tiles: two tile rows per item; 1000 / 1080: odd tile counts (125, 135), rows only 8-byte aligned; 258, 480, 514, 770 tiles: 2, 2, 3, 4 chunks
+    for case in range(28):
         n = int(rng.randint(1, 6))
         h = int(rng.choice([8, 16, 24, 40, 64, 72, 136, 270]))
         w = widths[case % len(widths)]

@@ -35,8 +35,9 @@
 //     extract kernel ORs each warp's ballot into (at most two) words of a zeroed raw-bit array
 //     and the embed kernel funnel-shifts its 32 watermark bits out of two words.
 //
-// Requirements (otherwise the launcher uses the vectorised-load kernels): planar uint8, at least 64
-// and an even number of tiles per row, base, pitch and frame stride multiples of 16 bytes.
+// Requirements (otherwise the launcher uses the vectorised-load kernels): planar uint8, at least 64 tiles
+// per row, base and frame stride multiples of 16 bytes, and either tight rows of at most 256 tiles (any
+// parity, e.g. portrait 1080 x 1920) or 16-byte aligned rows with an even number of tiles.
 #include "common.cuh"
 #include "svd4.cuh"
 #include "dwtsvd_tile.cuh"
@@ -449,16 +450,22 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
 static int strip_chunks(const TileGeom& g, int* chunk_tiles) {
     const int chunks = (g.tiles_x + kMaxStripTiles - 1) / kMaxStripTiles;
     int per = (g.tiles_x + chunks - 1) / chunks;
-    per += per & 1;                                   // even: 16-byte aligned chunk starts
+    if (chunks > 1) per += per & 1;                   // even: 16-byte aligned chunk starts
     *chunk_tiles = per;
     return (g.tiles_x + per - 1) / per;
 }
 
+// Two ways in.  A strip that is contiguous in global memory (tight rows covered exactly by tiles, at most 256
+// tiles per row) moves as one bulk copy of 8 * pitch bytes, which is a multiple of 16 whatever the width: this
+// also takes planes whose rows are only 8-byte aligned or hold an odd number of tiles (portrait 1080 x 1920:
+// 135 tiles per row).  Everything else moves row by row and needs 16-byte aligned rows and chunk starts.
 bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const TileGeom& g) {
-    if (!(pl->dtype == B200WM_U8 && pl->elem_stride == 1 && (pl->pitch_bytes % 16) == 0 && ((uintptr_t)a % 16) == 0 &&
-          ((uintptr_t)b % 16) == 0 && (pl->frame_stride_bytes % 16) == 0 && g.tiles_x >= 64 && (g.tiles_x % 2) == 0 && g.tiles_y > 0))
+    if (!(pl->dtype == B200WM_U8 && pl->elem_stride == 1 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 &&
+          (pl->frame_stride_bytes % 16) == 0 && g.tiles_x >= 64 && g.tiles_y > 0))
         return false;
     if (pl->n_frames > 1 && pl->frame_stride_bytes < pl->pitch_bytes * (long long)pl->height) return false;
+    const bool whole = g.tiles_x <= kMaxStripTiles && pl->pitch_bytes == 8ll * g.tiles_x;
+    if (!whole && ((pl->pitch_bytes % 16) != 0 || (g.tiles_x % 2) != 0)) return false;
     int chunk_tiles = 0;
     const long long frame_items = (long long)g.tiles_y * strip_chunks(g, &chunk_tiles);     // (narrow planes: about half of it)
     const long long items = pl->n_frames * frame_items;
