@@ -182,3 +182,23 @@ def test_owned_segment_vote_combine_world_size_2_gloo():
             want_p, want_f = _reference_vote(pats, L)
             assert pattern == want_p and freq == want_f and frames == len(pats), (rank, s)
             assert votes == [sum((p >> (L - 1 - j)) & 1 for p in pats) for j in range(L)]
+
+
+def test_fingerprint_payload_schemes_and_decisions():
+    """Host half of the fingerprint layer: the reference's payload schemes (tests/segment_mark_detect_hls.py:42-55,
+    tests/mark_video_to_hls.py:27-43), their inverse (tests/detect_watermarks.py:145-172) and the copy sequence /
+    fingerprint string (:404-425) - against the oracle's restatement."""
+    from offmark_b200 import fingerprint as fp
+    from oracle import payload as o_pay
+    for seg in (0, 1, 15, 16, 17, 255, 256, 300):
+        assert np.array_equal(fp.generate_payload_for_segment(seg), o_pay.payload_for_segment(seg))
+        for copy in (0, 3, 15, 16):
+            p = fp.generate_payload_for_segment(seg, copy)
+            assert np.array_equal(p, o_pay.payload_for_segment_copy(seg, copy))
+            assert fp.decode_watermark_pattern(p) == (seg % 16, copy % 16) == o_pay.segment_copy_from_pattern(p)
+    assert fp.decode_watermark_pattern(None) == (None, None) and fp.decode_watermark_pattern([0, 1, 1]) == (None, None)
+    results = [{"segment_number": 2, "detected_copy_index": 1}, {"segment_number": 0, "detected_copy_index": 3},
+               {"segment_number": 1, "detected_copy_index": 0}]
+    assert fp.copy_fingerprint(results) == ([3, 0, 1], "301")
+    results[1]["detected_copy_index"] = None
+    assert fp.copy_fingerprint(results) == ([None, 0, 1], None)
