@@ -22,8 +22,8 @@
 //     occupy registers for the length of the SVD.
 //   * Narrow planes (at most 128 tiles per row, e.g. the 960-wide chroma planes of 1080p yuv420p) take
 //     two tile rows per work item, so that both packed lanes of every thread stay busy.
-//   * Consumer thread t owns TWO tiles of the strip, t and t + 128 (narrow planes: tile t of the first
-//     and of the second tile row), and runs the eigen-iteration for both in packed FP32
+//   * Consumer thread t owns TWO tiles of the strip, t and t + half (half = half the tiles of the strip; narrow
+//     planes: tile t of the first and of the second tile row), and runs the eigen-iteration for both in packed FP32
 //     (FFMA2/FMUL2/FADD2, svd4x2.cuh): the kernels were issue-bound, and a packed instruction does the
 //     work of two for one issue slot.  It reads its 8x8 bytes from shared memory (conflict-free: a warp
 //     reads 256 contiguous bytes per row).  Embed updates the strip in
@@ -37,14 +37,15 @@
 //
 // Requirements (otherwise the launcher uses the vectorised-load kernels): planar uint8, at least 64 tiles
 // per row, base and frame stride multiples of 16 bytes, and either tight rows of at most 256 tiles (any
-// parity, e.g. portrait 1080 x 1920) or 16-byte aligned rows with an even number of tiles.
+// parity) or 16-byte aligned rows with an even number of tiles; rows of 129..183 tiles are left to the
+// vectorised-load kernels, which measured faster there.
 #include "common.cuh"
 #include "svd4.cuh"
 #include "dwtsvd_tile.cuh"
 
 namespace b200wm {
 
-constexpr int kStripThreads = 128;                 // consumer threads: two 8x8 tiles each (t and t + 128)
+constexpr int kStripThreads = 128;                 // consumer threads: two 8x8 tiles each (t and t + half)
 constexpr int kMaxStripTiles = 2 * kStripThreads;
 constexpr int kConsumerWarps = kStripThreads / 32;
 constexpr int kCtaThreads = kStripThreads + 32;    // + the producer warp
@@ -232,10 +233,15 @@ struct TilePair {
             hi_delta = (unsigned)sg.g.tiles_x;
             off_hi = live_hi ? 8u * slot_pitch + (unsigned)t * 8u : 0u;
         } else {
-            live_hi = t + kStripThreads < it.tiles;
-            warp_live_hi = ((t + kStripThreads) & ~31) < it.tiles;
-            hi_delta = kStripThreads;
-            off_hi = live_hi ? (unsigned)(t + kStripThreads) * 8u : 0u;
+            // the strip's tiles are split in two equal halves, so that planes with 129..255 tiles per row (720p: 160,
+            // portrait 1080p: 135) keep both packed lanes busy in fewer warps instead of leaving the upper lane idle
+            const int half = (it.tiles + 1) >> 1;
+            live_lo = t < half;
+            warp_live_lo = (t & ~31) < half;
+            live_hi = live_lo && t + half < it.tiles;
+            warp_live_hi = warp_live_lo && (t & ~31) + half < it.tiles;
+            hi_delta = (unsigned)half;
+            off_hi = live_hi ? (unsigned)(t + half) * 8u : 0u;
         }
         off_lo = live_lo ? (unsigned)t * 8u : 0u;
     }
@@ -326,9 +332,9 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
             }
         }
         if (ex.pos_counts && lane < L) {
-            // lane i sees the bits of blocks c+i, c+i+L, ...: payload position (c + i) mod L.  The halves are
-            // 128 blocks apart (a multiple of L) except on narrow planes, where they are one tile row apart.
-            if (kNarrow) {
+            // lane i sees the bits of blocks c+i, c+i+L, ...: payload position (c + i) mod L.  When the distance between
+            // the halves is a multiple of L (1080p: 120 blocks) both land on the same position.
+            if (kNarrow || (tp.hi_delta & (unsigned)(L - 1))) {
                 const int n0 = __popc(ballot_lo & (ex.every << lane)), n1 = __popc(ballot_hi & (ex.every << lane));
                 if (n0) atomicAdd(&cta_counts[stage][(c0 + lane) & (unsigned)(L - 1)], n0);
                 if (n1) atomicAdd(&cta_counts[stage][(c1 + lane) & (unsigned)(L - 1)], n1);
@@ -457,13 +463,16 @@ static int strip_chunks(const TileGeom& g, int* chunk_tiles) {
 
 // Two ways in.  A strip that is contiguous in global memory (tight rows covered exactly by tiles, at most 256
 // tiles per row) moves as one bulk copy of 8 * pitch bytes, which is a multiple of 16 whatever the width: this
-// also takes planes whose rows are only 8-byte aligned or hold an odd number of tiles (portrait 1080 x 1920:
-// 135 tiles per row).  Everything else moves row by row and needs 16-byte aligned rows and chunk starts.
+// also takes planes whose rows are only 8-byte aligned or hold an odd number of tiles.  Everything else moves row by row and needs 16-byte aligned rows and chunk starts.
 bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const TileGeom& g) {
     if (!(pl->dtype == B200WM_U8 && pl->elem_stride == 1 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 &&
           (pl->frame_stride_bytes % 16) == 0 && g.tiles_x >= 64 && g.tiles_y > 0))
         return false;
     if (pl->n_frames > 1 && pl->frame_stride_bytes < pl->pitch_bytes * (long long)pl->height) return false;
+    // Strips of 129..183 tiles (720p: 160, portrait 1080p: 135) carry too few bytes per work item for four CTAs
+    // of four consumer warps to keep the SM busy: measured 0.59-0.77 of peak against 0.79 for the vectorised-load
+    // kernels (scripts/midwidth_probe.py), so those planes stay on that path until the CTA shape is specialised.
+    if (g.tiles_x > kStripThreads && g.tiles_x < 184) return false;
     const bool whole = g.tiles_x <= kMaxStripTiles && pl->pitch_bytes == 8ll * g.tiles_x;
     if (!whole && ((pl->pitch_bytes % 16) != 0 || (g.tiles_x % 2) != 0)) return false;
     int chunk_tiles = 0;
