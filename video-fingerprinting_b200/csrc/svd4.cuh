@@ -194,7 +194,6 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
         float H[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) H[k] = G[k];
-        float lam_prev = -1.0f;
 #pragma unroll 1
         for (int round = 0; round < kSquarings && !done; ++round) {
             square_sym4(H);
@@ -207,11 +206,11 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
             symv4(G, x, w);
             done = rayleigh_check(x, w, tr, xw, xx);
             // A block that is not dominated (2 lambda_0 <= tr G: noise-like content, flat chroma) can never be
-            // certified.  Once its Rayleigh quotient has stopped moving while 2 lambda <= tr there is no point in
-            // squaring further: leave for the direct solver now instead of after all kSquarings rounds.
-            const float lam = xw / xx;
-            if (!done && 2.0f * lam <= tr && fabsf(lam - lam_prev) <= 1e-6f * lam) break;
-            lam_prev = lam;
+            // certified.  After three squaring rounds the iterate has seen G^16: if the Rayleigh quotient is still
+            // not above tr/2 the block leaves for the direct solver now instead of after all kSquarings rounds
+            // (a barely dominated block that would have been certified later takes the direct solver too: same
+            // sigma_0 to float32 accuracy).
+            if (!done && round >= 2 && !(2.0f * xw > tr * xx)) break;
         }
     }
     if (done) {
