@@ -18,7 +18,7 @@ else
   cp video-fingerprinting_b200/lib/libb200wm.so /tmp/libb200wm_default.so
   for v in gpurun_variants/libb200wm_*.so; do
     cp $v video-fingerprinting_b200/lib/libb200wm.so
-    python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
+    python bench.py ${VARIANT_BENCH_ARGS} --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernels']
 print('$v', 'fps', round(d['value']), 'embed_ms', round(k['embed_ms'],3), 'extract_ms', round(k['extract_ms'],3), 'acc', d['bit_accuracy']['frames_exact'])"

@@ -27,8 +27,10 @@ namespace b200wm {
 // kernels
 // ------------------------------------------------------------------------------------------
 // grid = (ceil(words / warps_per_cta), frames in this launch); one warp = one word of raw bits.
+// mode 0 is capped at 64 registers (8 CTAs of 128 threads per SM): measured 2.29 ms per 3000 1080p frames against
+// 2.46 ms at 80 and 2.63 ms uncapped; the generic modes need their registers
 template <int kMode>   // 0: u8 fast, 1: u8 generic, 2: f32 generic
-__global__ void __launch_bounds__(kThreads) dwtsvd_embed_kernel(PlaneArgs pl, EmbedArgs em, TileGeom g, int frame0) {
+__global__ void __launch_bounds__(kThreads, kMode == 0 ? 8 : 1) dwtsvd_embed_kernel(PlaneArgs pl, EmbedArgs em, TileGeom g, int frame0) {
     const int frame = frame0 + blockIdx.y;
     const unsigned c = blockIdx.x * kThreads + threadIdx.x;
     if (c >= (unsigned)g.n_tiles) return;
