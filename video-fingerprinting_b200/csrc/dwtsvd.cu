@@ -159,7 +159,10 @@ __device__ __forceinline__ TileAddr tile_addr(unsigned c, int frame, const Plane
     return a;
 }
 
-__global__ void __launch_bounds__(kThreads) dwtsvd_extract_x2_kernel(PlaneArgs pl, ExtractArgs ex, TileGeom g, int frame0) {
+#ifndef B200WM_LDG_EXTRACT_MIN_CTAS
+#define B200WM_LDG_EXTRACT_MIN_CTAS 6      // 80 registers: 1.03 ms per 3000 1080p frames (1.06 uncapped, 1.07 at 64)
+#endif
+__global__ void __launch_bounds__(kThreads, B200WM_LDG_EXTRACT_MIN_CTAS) dwtsvd_extract_x2_kernel(PlaneArgs pl, ExtractArgs ex, TileGeom g, int frame0) {
     const int frame = frame0 + blockIdx.y;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned base = (blockIdx.x * (kThreads / 32) + warp) * 64;
