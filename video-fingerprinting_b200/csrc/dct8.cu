@@ -21,6 +21,14 @@
 namespace b200wm {
 
 constexpr int kDctThreads = 128;
+// register caps of the vector-load instantiations (scripts/dct8_probe.py: embed 0.68 -> 0.73 of peak at 5 CTAs per SM,
+// worse at 6 and 8; masks 0.26 -> 0.27 at 6-8)
+#ifndef B200WM_DCT_MASKS_MIN_CTAS
+#define B200WM_DCT_MASKS_MIN_CTAS 6
+#endif
+#ifndef B200WM_DCT_EMBED_MIN_CTAS
+#define B200WM_DCT_EMBED_MIN_CTAS 5
+#endif
 
 template <typename T>
 __device__ __forceinline__ void load_block(const uint8_t* p, long long pitch, int es, float (&b)[64]) {
@@ -126,7 +134,7 @@ __device__ __forceinline__ float texture_mask(const float (&c)[64]) {
 }
 
 template <typename T, bool kVec>
-__global__ void __launch_bounds__(kDctThreads) dct8_masks_kernel(DctPlane pl, BlockGeom g, float* __restrict__ block_mean,
+__global__ void __launch_bounds__(kDctThreads, kVec ? B200WM_DCT_MASKS_MIN_CTAS : 1) dct8_masks_kernel(DctPlane pl, BlockGeom g, float* __restrict__ block_mean,
                                                                  float* __restrict__ tex_mask,
                                                                  double* __restrict__ frame_sum, int frame0) {
     const int frame = frame0 + blockIdx.y;
@@ -204,7 +212,7 @@ struct DctWm {
 };
 
 template <typename T, bool kVec>
-__global__ void __launch_bounds__(kDctThreads) dct8_embed_kernel(DctPlane pl, BlockGeom g, const float* __restrict__ block_mean,
+__global__ void __launch_bounds__(kDctThreads, kVec ? B200WM_DCT_EMBED_MIN_CTAS : 1) dct8_embed_kernel(DctPlane pl, BlockGeom g, const float* __restrict__ block_mean,
                                                                  const float* __restrict__ tex_mask,
                                                                  const double* __restrict__ frame_sum, DctWm wm, int frame0) {
     const int frame = frame0 + blockIdx.y;
