@@ -127,3 +127,20 @@ def test_gpu_resize_roundtrip_and_errors(marked_frames):
         ops.attack_resize(t, (W * 2, H * 2), ops.INTER_AREA)
     with pytest.raises(Exception):
         ops.attack_resize(t, (W // 2, H // 2), 2)    # INTER_CUBIC
+
+
+def test_gpu_resize_random_geometries():
+    """Seeded sweep over odd sizes and ratios: b200wm_attack_resize stays bit-identical to cv2.resize."""
+    import cv2
+    from b200wm import ops
+    rng = np.random.RandomState(2026)
+    for _ in range(40):
+        sh, sw = int(rng.randint(2, 90)), int(rng.randint(2, 120))
+        dh, dw = int(rng.randint(1, sh + 1)), int(rng.randint(1, sw + 1))
+        src = rng.randint(0, 256, (sh, sw)).astype(np.uint8)
+        t = torch.from_numpy(src).to(DEV)
+        got = ops.attack_resize(t, (dw, dh), ops.INTER_AREA).cpu().numpy()
+        assert np.array_equal(got, cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA)), ((sh, sw), (dh, dw))
+        uh, uw = int(rng.randint(1, 140)), int(rng.randint(1, 160))
+        got = ops.attack_resize(t, (uw, uh), ops.INTER_LINEAR).cpu().numpy()
+        assert np.array_equal(got, cv2.resize(src, (uw, uh), interpolation=cv2.INTER_LINEAR)), ((sh, sw), (uh, uw))

@@ -163,3 +163,20 @@ def test_resize_restatement_is_cv2_bit_for_bit(src_hw, dst_hw):
     assert np.array_equal(attacks.resize_linear_restated(small, (src_hw[1], src_hw[0])), back)
     # bilinear reductions too (the kernel is not limited to enlarging)
     assert np.array_equal(attacks.resize_linear_restated(src, dsize), cv2.resize(src, dsize, interpolation=cv2.INTER_LINEAR))
+
+
+def test_resize_restatement_random_geometries():
+    """Seeded sweep over odd sizes and ratios (integer, 2x2, 1.5, irrational-looking): the restatement of
+    cv2.resize that the CUDA kernels follow stays bit-identical to OpenCV."""
+    import cv2
+    from oracle import attacks
+    rng = np.random.RandomState(2026)
+    for _ in range(40):
+        sh, sw = int(rng.randint(2, 90)), int(rng.randint(2, 120))
+        dh, dw = int(rng.randint(1, sh + 1)), int(rng.randint(1, sw + 1))
+        src = rng.randint(0, 256, (sh, sw)).astype(np.uint8)
+        want = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA)
+        assert np.array_equal(attacks.resize_area_restated(src, (dw, dh)), want), ((sh, sw), (dh, dw))
+        uh, uw = int(rng.randint(1, 140)), int(rng.randint(1, 160))
+        want = cv2.resize(src, (uw, uh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(attacks.resize_linear_restated(src, (uw, uh)), want), ((sh, sw), (uh, uw))
