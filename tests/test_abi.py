@@ -106,3 +106,15 @@ def test_plain_c_caller_recovers_the_payload(tmp_path):
     proc = subprocess.run([_build_c_demo(tmp_path)], capture_output=True, text=True, timeout=120)
     assert proc.returncode == 0, proc.stdout + proc.stderr
     assert "recovered payload: 0 1 1 0 0 1 0 1" in proc.stdout and "matches" in proc.stdout
+
+
+def test_ctypes_prototypes_have_the_headers_parameter_counts():
+    """Every binding in b200wm/_lib.py declares as many arguments as the C prototype in include/b200wm.h."""
+    from b200wm import _lib
+    text = open(os.path.join(ROOT, "include", "b200wm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for m in re.finditer(r"B200WM_API\s+[\w\s\*]+?\b(b200wm_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert name in _lib.PROTOTYPES, name
+        assert len(_lib.PROTOTYPES[name][1]) == n, f"{name}: header has {n} parameters, binding {len(_lib.PROTOTYPES[name][1])}"
