@@ -4,7 +4,10 @@
 All frames are generated, marked, attacked and read back on the GPU (b200wm kernels); on a
 subsample per attack the reference extractor (oracle restatement, CPU) reads the very same attacked
 frames so that the two bit-error rates can be put side by side.  Prints a markdown table.
-    python scripts/attack_study.py [--frames 10000] [--oracle-frames 32]
+    python tests/studies/attack_study.py [--frames 10000] [--oracle-frames 32]
+
+Lives under tests/ because it runs the oracle (as the checker) next to the CUDA path: only tests/, smoke() and
+bench.py's CPU legs may do that.
 """
 import argparse
 import json
@@ -12,7 +15,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "video-fingerprinting_b200"))
 
