@@ -271,7 +271,21 @@ B200WM_API int b200wm_dwtsvd_detect_host(const uint8_t* src_host, const b200wm_p
                              const int32_t* perm_host, uint8_t* patterns_host, uint32_t* raw_bits_host,
                              int32_t* pos_counts_host, int32_t chunk_frames);
 
-/* Streams and device scratch of the two calls above persist between calls (per device, grow-only); this
+/*
+ * mark + verify with ONE trip over the link: upload, embed, extract + per-frame vote on the marked chunk while
+ * it is still in device memory, download the marked planes: 2*W*H bytes per frame on PCIe instead of the 3*W*H
+ * of the two calls above.  This is the reference's own "watermark, then always verify" step
+ * (tests/mark_video_to_hls.py:356-399 re-decodes every marked segment through detect_patterns_in_segment,
+ * :253-266; tests/segment_mark_detect_hls.py:195-243).  Outputs as mark (dst_host) and detect (patterns_host,
+ * optional raw_bits_host / pos_counts_host); the patterns are those of the MARKED planes.
+ */
+B200WM_API int b200wm_dwtsvd_mark_verify_host(const uint8_t* src_host, uint8_t* dst_host, const b200wm_plane* plane,
+                                  const uint32_t* wm_packed_host, int32_t n_wm_rows, int32_t wm_words, int64_t wm_len,
+                                  const int32_t* frame_wm_row_host, float scale, int32_t payload_len, const int32_t* perm_host,
+                                  uint8_t* patterns_host, uint32_t* raw_bits_host, int32_t* pos_counts_host,
+                                  int32_t chunk_frames);
+
+/* Streams and device scratch of the calls above persist between calls (per device, grow-only); this
  * frees them for the current device. */
 B200WM_API int b200wm_host_scratch_release(void);
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import bracket, dwt_dct_svd as o_svd, payload as o_pay, synth
-from parity import PAYLOAD, KEY, knife_edge_blocks, tile_mask_to_pixels
+from parity import PAYLOAD, KEY, knife_edge_blocks, tile_mask_to_pixels, flat_tiles
 
 pytestmark = pytest.mark.gpu
 
@@ -78,9 +78,13 @@ def test_extract_full_range_content_incl_flat_and_zero_blocks():
     plane = synth.full_range_plane_u8(256, 384, 11)
     want = o_svd.extract_plane(plane)
     got = _extract_bits(torch.from_numpy(plane).to(_dev()), want.size)
-    n_diff = _assert_bits_match(got, want, plane.astype(np.float32), "full range")
-    # flat 255 blocks have sigma_0 = 2040 = 136*15 exactly: boundary cases by construction
-    assert n_diff <= want.size
+    _assert_bits_match(got, want, plane.astype(np.float32), "full range")
+    # The flat 255 quarter: exact sums give sigma_0 = 2040 = 136*15, a boundary; the reference's float32 Haar band
+    # gives 2039.99988 -> bit 1.  The kernels follow the reference on flat tiles (dwtsvd_tile.cuh), unmasked:
+    flat = flat_tiles(plane)
+    assert flat.sum() > 100 and np.array_equal(got[0, :flat.size][flat], want[0, :flat.size][flat].astype(np.uint8))
+    white = flat & (plane[::8, ::8][:plane.shape[0] // 8, :plane.shape[1] // 8].reshape(-1) == 255)
+    assert white.any() and (got[0, :flat.size][white] == 1).all()
 
 
 def test_sigma_matches_float64_truth():
@@ -155,12 +159,16 @@ def test_embed_full_range_clips_like_reference():
     ca, _ = __import__("oracle.haar", fromlist=["x"]).dwt2_haar(yuv[:, :, 1])
     blocks, _, _ = o_svd._to_blocks(ca, 4)
     s = np.linalg.svd(blocks.astype(np.float64), compute_uv=False)
-    ambiguous = (s[:, 0] - s[:, 1]) < 1e-3 * np.maximum(s[:, 0], 1e-30)
+    ambiguous = ((s[:, 0] - s[:, 1]) < 1e-3 * s[:, 0]) & (s[:, 0] > 0)      # all-zero blocks are NOT masked: svd(0) is exact
     ok_px = ~tile_mask_to_pixels(edge_floor | ambiguous, plane.shape)
     assert diff[ok_px].max(initial=0) <= 1
-    # all-zero blocks: svd(0) = (I, 0, I) puts the mark on the DC term -> +1 where the bit is 1
-    zero_tiles = (s[:, 0] == 0)
-    assert zero_tiles.any()
+    assert (edge_floor | ambiguous).mean() < 2e-3, (edge_floor.mean(), ambiguous.mean())
+    # all-zero blocks: svd(0) = (I, 0, I) puts the mark on the DC term -> +0 / +1 for bit 0 / 1, exactly like the
+    # reference; flat 255 blocks: the reference's floor is 135 (sigma_0 = 2039.99988), -1 / 0 for bit 0 / 1 - unmasked
+    flat = tile_mask_to_pixels(flat_tiles(plane), plane.shape)
+    assert flat.sum() > 64 * 100 and np.array_equal(got[flat], want[flat])
+    zero_px = tile_mask_to_pixels(s[:, 0] == 0, plane.shape)
+    assert zero_px.any() and set(np.unique(got[zero_px])) == {0, 1}
 
 
 def test_embed_out_of_place_and_per_frame_rows():
@@ -278,7 +286,7 @@ def test_no_out_of_bounds_writes_guard_bytes():
     inside a larger buffer whose guard bytes (before, after, and the chroma planes between the luma
     planes of an I420 layout) must come back untouched from embed and extract, on both kernel paths."""
     from b200wm import ops
-    n, h, w = 5, 72, 1040                       # 130 tiles per row: TMA-eligible, 9 tile rows
+    n, h, w = 5, 72, 1536                       # 192 tiles per row: TMA-eligible, 9 tile rows
     frame_bytes = h * w * 3 // 2
     guard = 4096
     buf = torch.full((guard + n * frame_bytes + guard,), 0xA5, dtype=torch.uint8, device=_dev())
@@ -492,3 +500,74 @@ def test_full_1080p_parity_across_content_classes(name):
     perm = torch.from_numpy(o_pay.permutation(8, KEY).astype(np.int32)).to(_dev())
     patterns, _ = ops.vote_finish(counts, h * w // 64, perm)
     assert np.array_equal(patterns[0].cpu().numpy(), o_pay.degenerate(want_bits, 8, KEY)), name
+
+
+# ---- deterministic cases that no mask hides: all-zero and flat planes ---------------------------------------
+FLAT_VALUES = (0, 1, 15, 16, 30, 45, 120, 128, 235, 240, 255)      # 15k/8-multiples sit ON a floor boundary (sigma_0 = 8v)
+
+
+@pytest.mark.parametrize("h,w", [(64, 1920), (64, 2048), (32, 960), (16, 3840), (40, 72)])
+def test_zero_and_flat_planes_equal_the_oracle_exactly(h, w):
+    """All-zero and flat planes, payload bits 0 and 1: the reference is deterministic here (svd(0) = (I, 0, I);
+    a constant block is exact in cv2.dct and LAPACK, sigma_0 = 16*fl(c*fl(c*v)) with the float32 Haar tap c),
+    so marked planes and raw bits must EQUAL the oracle's - no tolerance, no mask - on the TMA kernels (whole
+    strips, narrow planes, column chunks) and the vectorised-load kernels.  The marked planes are flat again
+    (uniform increment), so extracting from them exercises the same rule a second time."""
+    from b200wm import ops
+    n = h * w // 64
+    wm = _wm((h, w))[0]
+    packed, nb = ops.pack_bits(np.stack([wm, np.zeros_like(wm), np.ones_like(wm)]), device=_dev())
+    planes = np.stack([np.full((h, w), v, dtype=np.uint8) for v in FLAT_VALUES])
+    src = torch.from_numpy(planes).to(_dev())
+    clean_bits = _extract_bits(src, n)
+    for row, bits_row in enumerate((wm, np.zeros_like(wm), np.ones_like(wm))):
+        t = src.clone()
+        ops.dwtsvd_embed_(t, packed, nb, frame_wm_row=torch.full((len(FLAT_VALUES),), row, dtype=torch.int32, device=_dev()))
+        got = t.cpu().numpy()
+        marked_bits = _extract_bits(t, n)
+        for k, v in enumerate(FLAT_VALUES):
+            want = o_svd.embed_plane_u8(planes[k], bits_row)
+            assert np.array_equal(got[k], want), (v, row, np.unique(got[k].astype(int) - want))
+            assert np.array_equal(marked_bits[k], o_svd.extract_plane(want)[0]), (v, row)
+    for k, v in enumerate(FLAT_VALUES):
+        assert np.array_equal(clean_bits[k], o_svd.extract_plane(planes[k])[0]), v
+
+
+def test_piecewise_flat_planes_every_level_and_layout():
+    """One flat tile per grey level 0..255 (twice over): uint8 aligned, uint8 unaligned (generic kernels) and the
+    reference's float32 interleaved layout, embed and extract EQUAL the oracle (float32 within 1e-4, the
+    synthesis rounding of idwt2)."""
+    from b200wm import ops
+    rng = np.random.RandomState(3)
+    levels = np.concatenate([np.arange(256), rng.permutation(256)]).reshape(8, 64)
+    plane = np.kron(levels, np.ones((8, 8))).astype(np.uint8)              # 64 x 512
+    h, w = plane.shape
+    n = h * w // 64
+    wm = _wm((h, w))
+    packed, nb = ops.pack_bits(wm[0], device=_dev())
+    want = o_svd.embed_plane_u8(plane, wm[0])
+    want_bits = o_svd.extract_plane(plane)[0]
+    # aligned
+    t = torch.from_numpy(plane.copy()).to(_dev())
+    assert np.array_equal(_extract_bits(t, n)[0], want_bits)
+    ops.dwtsvd_embed_(t, packed, nb)
+    assert np.array_equal(t.cpu().numpy(), want)
+    assert np.array_equal(_extract_bits(t, n)[0], o_svd.extract_plane(want)[0])
+    # unaligned view
+    big = torch.zeros((h + 2, w + 13), dtype=torch.uint8, device=_dev())
+    view = big[1:h + 1, 5:w + 5]
+    view.copy_(torch.from_numpy(plane))
+    assert np.array_equal(_extract_bits(view, n)[0], want_bits)
+    ops.dwtsvd_embed_(view, packed, nb)
+    assert np.array_equal(view.cpu().numpy(), want)
+    # float32 interleaved, channel 1 (negative and fractional flat values as well)
+    yuv = np.zeros((h, w, 3), dtype=np.float32)
+    yuv[:, :, 1] = plane.astype(np.float32) * 0.47 - 60.25
+    want_f = o_svd.encode(yuv.copy(), wm)
+    tf = torch.from_numpy(yuv.copy()).to(_dev())
+    raw, _ = ops.dwtsvd_extract(tf, channel=1)
+    assert np.array_equal(ops.unpack_bits(raw, n)[0], o_svd.decode(yuv)[0])
+    ops.dwtsvd_embed_(tf, packed, nb, channel=1)
+    np.testing.assert_allclose(tf.cpu().numpy()[:, :, 1], want_f[:, :, 1], rtol=0, atol=1e-4)
+    raw, _ = ops.dwtsvd_extract(torch.from_numpy(want_f).to(_dev()), channel=1)
+    assert np.array_equal(ops.unpack_bits(raw, n)[0], o_svd.decode(want_f)[0])

@@ -78,3 +78,29 @@ def test_batched_frames_and_scales():
     for f in range(3):
         want = bracket.mark_frame(frames[f], lambda y: o_svd.encode(y, wm, scales=(20, 15, 0)))
         assert np.abs(got[f].astype(np.int16) - want).max() <= 1
+
+
+def test_flat_colour_tiles_follow_the_reference_exactly():
+    """Flat tiles are deterministic in the reference (tests/parity.py): frames made of flat 8x8 colour patches -
+    grey ones included, whose U is 0.5 and whose sigma_0 = 4 - 2e-7 sits ON a boundary for scale 4 - must give
+    the oracle's raw bits with no mask, clean and marked, and marked frames within 1 LSB."""
+    from b200wm import ops
+    rng = np.random.RandomState(8)
+    h, w = 64, 256
+    colours = rng.randint(0, 256, (h // 8, w // 8, 3)).astype(np.uint8)
+    colours[::2, ::2] = colours[::2, ::2, :1]                      # a quarter of the patches grey
+    frame = np.kron(colours, np.ones((8, 8, 1), dtype=np.uint8))
+    n = h * w // 64
+    wm = o_pay.generate_wm(PAYLOAD, (1, n), KEY)
+    packed, nb = ops.pack_bits(wm[0], device=DEV)
+    for scale in (15.0, 4.0):
+        scales = (0, scale, 0)
+        raw, _ = ops.dwtsvd_extract_rgb8(torch.from_numpy(frame).to(DEV), scale=scale)
+        assert np.array_equal(ops.unpack_bits(raw, n)[0], o_svd.decode(bracket.to_yuv(frame), scales=scales)[0]), scale
+        want = bracket.mark_frame(frame, lambda y: o_svd.encode(y, wm, scales=scales))
+        t = torch.from_numpy(frame.copy()).to(DEV)
+        ops.dwtsvd_embed_rgb8_(t, packed, nb, scales=scales)
+        got = t.cpu().numpy()
+        assert np.abs(got.astype(np.int16) - want).max() <= 1, scale
+        raw, _ = ops.dwtsvd_extract_rgb8(torch.from_numpy(want).to(DEV), scale=scale)
+        assert np.array_equal(ops.unpack_bits(raw, n)[0], o_svd.decode(bracket.to_yuv(want), scales=scales)[0]), scale

@@ -180,3 +180,20 @@ def test_resize_restatement_random_geometries():
         uh, uw = int(rng.randint(1, 140)), int(rng.randint(1, 160))
         want = cv2.resize(src, (uw, uh), interpolation=cv2.INTER_LINEAR)
         assert np.array_equal(attacks.resize_linear_restated(src, (uw, uh)), want), ((sh, sw), (uh, uw))
+
+
+def test_flat_blocks_are_exact_in_the_reference_restatement():
+    """The rule the kernels use for flat tiles on a quantisation boundary (csrc/dwtsvd_tile.cuh:flat_sigma_ref):
+    on a constant block the float32 Haar band is 4*fl(c*fl(c*v)) per coefficient and cv2.dct + LAPACK are exact,
+    so sigma_0 = 16*fl(c*fl(c*|v|)) - for every uint8 level and for float samples (chroma can be negative)."""
+    from oracle import dwt_dct_svd as o_svd
+    c = np.float32(1.0 / np.sqrt(2.0))
+    values = [np.float32(v) for v in range(256)] + list(np.random.RandomState(0).uniform(-100, 100, 200).astype(np.float32))
+    for v in values:
+        yuv = np.zeros((8, 8, 3), dtype=np.float32)
+        yuv[:, :, 1] = v
+        s32, _ = o_svd.decode_sigma(yuv)
+        assert s32[0] == np.float32(16) * (c * (c * np.abs(v))), v
+    # the case that motivated it: flat 255 reads as bit 1 (sigma_0 = 2039.99988, not 2040 = 136 * 15)
+    assert o_svd.extract_plane(np.full((8, 8), 255, dtype=np.uint8))[0, 0] == 1.0
+    assert o_svd.extract_plane(np.full((8, 8), 30, dtype=np.uint8))[0, 0] == 0.0

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "b200wm_dwtsvd_extract_rgb8": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),
     "b200wm_dwtsvd_mark_host": (C.c_int, [_vp, _vp, _PP, _vp, _i32, _i32, _i64, _vp, _f32, _i32]),
     "b200wm_dwtsvd_detect_host": (C.c_int, [_vp, _PP, _f32, _i32, _vp, _vp, _vp, _vp, _i32]),
+    "b200wm_dwtsvd_mark_verify_host": (C.c_int, [_vp, _vp, _PP, _vp, _i32, _i32, _i64, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _i32]),
     "b200wm_host_scratch_release": (C.c_int, []),
     "b200wm_attack_jpeg_requant": (C.c_int, [_vp, _vp, _PP, _i32, _vp]),
     "b200wm_attack_add_noise": (C.c_int, [_vp, _vp, _PP, _vp, _vp]),

@@ -415,6 +415,44 @@ def dwtsvd_detect_host(src, perm, scale=15.0, chunk_frames=0, want_raw_bits=Fals
     return patterns.numpy()
 
 
+def dwtsvd_mark_verify_host(src, dst, wm_rows, perm, scale=15.0, frame_wm_row=None, chunk_frames=0, wm_len=None,
+                            want_raw_bits=False):
+    """Mark host-resident planes AND read the payload back from the marked planes in the same pass (one upload, one
+    download per frame): the reference's mark-then-verify step (tests/mark_video_to_hls.py:356-399).  Arguments as
+    ``dwtsvd_mark_host`` plus the de-shuffling permutation; -> patterns uint8 ``[N, L]`` (numpy) [, raw bits]."""
+    require_cuda()
+    s, pl = _host_planes(src)
+    d, dpl = _host_planes(dst)
+    if (dpl.height, dpl.width, dpl.n_frames, dpl.pitch_bytes, dpl.frame_stride_bytes) != \
+            (pl.height, pl.width, pl.n_frames, pl.pitch_bytes, pl.frame_stride_bytes):
+        raise ValueError("dst must have the geometry of src")
+    if wm_len is None:
+        packed, n = pack_bits(wm_rows)
+    else:
+        packed, n = wm_rows, int(wm_len)
+        if not isinstance(packed, torch.Tensor) or packed.is_cuda or packed.dtype != torch.int32 or packed.dim() != 2 \
+                or not packed.is_contiguous():
+            raise ValueError("packed watermark rows must be a contiguous CPU int32 [rows, words] tensor")
+    rows = None
+    if frame_wm_row is not None:
+        rows = torch.as_tensor(frame_wm_row, dtype=torch.int32).contiguous()
+        if rows.numel() != pl.n_frames:
+            raise ValueError("frame_wm_row needs one entry per frame")
+    perm = torch.as_tensor(np.asarray(perm), dtype=torch.int32).contiguous()
+    length = perm.numel()
+    _, _, words = geometry(pl.height, pl.width)
+    patterns = torch.empty((pl.n_frames, length), dtype=torch.uint8)
+    raw = torch.empty((pl.n_frames, max(words, 1)), dtype=torch.int32) if want_raw_bits else None
+    check(lib.b200wm_dwtsvd_mark_verify_host(C.c_void_p(s.data_ptr()), C.c_void_p(d.data_ptr()), C.byref(pl),
+                                             C.c_void_p(packed.data_ptr()), packed.shape[0], packed.shape[1], int(n),
+                                             C.c_void_p(rows.data_ptr()) if rows is not None else None, float(scale), length,
+                                             C.c_void_p(perm.data_ptr()), C.c_void_p(patterns.data_ptr()),
+                                             C.c_void_p(raw.data_ptr()) if raw is not None else None, None, int(chunk_frames)))
+    if want_raw_bits:
+        return patterns.numpy(), raw[:, :words].numpy().view(np.uint32)
+    return patterns.numpy()
+
+
 def host_scratch_release():
     """Free the streams and device scratch that the host-buffer entry points keep between calls."""
     check(lib.b200wm_host_scratch_release())

@@ -37,6 +37,8 @@ int launch_embed_rgb8(const uint8_t*, uint8_t*, int, int, int, long long, long l
 int launch_extract_rgb8(const uint8_t*, int, int, int, long long, long long, int, float, uint32_t*, int, int, int32_t*, cudaStream_t);
 int mark_host(const uint8_t*, uint8_t*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float, int);
 int detect_host(const uint8_t*, const b200wm_plane*, float, int, const int32_t*, uint8_t*, uint32_t*, int32_t*, int);
+int mark_verify_host(const uint8_t*, uint8_t*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float, int,
+                     const int32_t*, uint8_t*, uint32_t*, int32_t*, int);
 int host_scratch_release();
 int launch_dwtsvd_sigma_dct(const void*, const b200wm_plane*, float*, cudaStream_t);
 void set_path(int);
@@ -211,6 +213,15 @@ B200WM_API int b200wm_dwtsvd_detect_host(const uint8_t* src_host, const b200wm_p
                              const int32_t* perm_host, uint8_t* patterns_host, uint32_t* raw_bits_host,
                              int32_t* pos_counts_host, int32_t chunk_frames) {
     return detect_host(src_host, plane, scale, payload_len, perm_host, patterns_host, raw_bits_host, pos_counts_host, chunk_frames);
+}
+
+B200WM_API int b200wm_dwtsvd_mark_verify_host(const uint8_t* src_host, uint8_t* dst_host, const b200wm_plane* plane,
+                                  const uint32_t* wm_packed_host, int32_t n_wm_rows, int32_t wm_words, int64_t wm_len,
+                                  const int32_t* frame_wm_row_host, float scale, int32_t payload_len, const int32_t* perm_host,
+                                  uint8_t* patterns_host, uint32_t* raw_bits_host, int32_t* pos_counts_host,
+                                  int32_t chunk_frames) {
+    return mark_verify_host(src_host, dst_host, plane, wm_packed_host, n_wm_rows, wm_words, wm_len, frame_wm_row_host, scale,
+                            payload_len, perm_host, patterns_host, raw_bits_host, pos_counts_host, chunk_frames);
 }
 
 }  // extern "C"

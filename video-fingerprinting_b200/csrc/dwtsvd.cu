@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(kThreads, kMode == 0 ? 8 : 1) dwtsvd_embed_ker
         load_tile_u8<false>(p, pl.pitch, rows, S);
         // bias 1.5*2^23: the FMA rounds the increment to the nearest integer (ties to even) and
         // leaves it, two's complement, in the low mantissa bits.
-        embed_deltas<true>(S, bit, em.scale, em.inv_scale, 12582912.0f, D, s_stash + threadIdx.x);
+        embed_deltas<true>(S, bit, em.scale, em.inv_scale, 12582912.0f, D, s_stash + threadIdx.x,
+                           [&]() { return flat_probe_global<uint8_t>(p, pl.pitch, 1); });
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             // 16-bit lanes: lo = increment of the left 2x2 of this word, hi = the right one
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, kMode == 0 ? 8 : 1) dwtsvd_embed_ker
         const uint8_t* p = pl.src + off + (long long)tx * 8 * es;
         uint8_t* o = pl.dst + off + (long long)tx * 8 * es;
         load_tile_generic<uint8_t>(p, pl.pitch, es, S);
-        embed_deltas<false>(S, bit, em.scale, em.inv_scale, 0.0f, D, nullptr);
+        embed_deltas<false>(S, bit, em.scale, em.inv_scale, 0.0f, D, nullptr, [&]() { return flat_probe_global<uint8_t>(p, pl.pitch, es); });
 #pragma unroll
         for (int y = 0; y < 8; ++y)
 #pragma unroll
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kThreads, kMode == 0 ? 8 : 1) dwtsvd_embed_ker
         const uint8_t* p = pl.src + off + (long long)tx * 8 * es * 4;
         uint8_t* o = pl.dst + off + (long long)tx * 8 * es * 4;
         load_tile_generic<float>(p, pl.pitch, es, S);
-        embed_deltas<false>(S, bit, em.scale, em.inv_scale, 0.0f, D, nullptr);
+        embed_deltas<false>(S, bit, em.scale, em.inv_scale, 0.0f, D, nullptr, [&]() { return flat_probe_global<float>(p, pl.pitch, es); });
 #pragma unroll
         for (int y = 0; y < 8; ++y) {
             const float* pr = reinterpret_cast<const float*>(row_ptr(p, y, pl.pitch));
@@ -112,7 +113,11 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_extract_kernel(PlaneArgs pl, 
             load_tile_generic<float>(pl.src + off + (long long)tx * 8 * pl.elem_stride * 4, pl.pitch, pl.elem_stride, S);
         }
         float sigma;
-        bit = extract_bit(S, ex.scale, ex.inv_scale, sigma);
+        bit = extract_bit(S, ex.scale, ex.inv_scale, sigma, [&]() {
+            if (kMode == 2) return flat_probe_global<float>(pl.src + off + (long long)tx * 8 * pl.elem_stride * 4, pl.pitch, pl.elem_stride);
+            return flat_probe_global<uint8_t>(pl.src + off + (long long)tx * 8 * (kMode == 0 ? 1 : pl.elem_stride), pl.pitch,
+                                              kMode == 0 ? 1 : pl.elem_stride);
+        });
         if (ex.sigma) ex.sigma[(long long)frame * g.n_tiles + c] = sigma;
     }
     const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
@@ -179,7 +184,8 @@ __global__ void __launch_bounds__(kThreads, B200WM_LDG_EXTRACT_MIN_CTAS) dwtsvd_
             }
             sums_from_rows_x2(ra, rb, S);
         }
-        bits = extract_bits_x2(S, ex.scale, ex.inv_scale);
+        bits = extract_bits_x2(S, ex.scale, ex.inv_scale,
+                               [&](int which) { return flat_probe_global<uint8_t>(pl.src + (which ? hi.off : lo.off), pl.pitch, 1); });
     }
     const unsigned ballot_lo = __ballot_sync(0xFFFFFFFFu, lo.live && (bits & 1u));
     const unsigned ballot_hi = __ballot_sync(0xFFFFFFFFu, hi.live && (bits & 2u));

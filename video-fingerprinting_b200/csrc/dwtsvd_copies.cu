@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_copies_kernel(PlaneArgs
         {
             float S[16];
             load_tile_u8<true>(pl.src + o0, pl.pitch, rows, S);
-            embed_prepare(S, em.scale, em.inv_scale, bp);
+            embed_prepare(S, em.scale, em.inv_scale, bp, [&]() { return flat_probe_global<uint8_t>(pl.src + o0, pl.pitch, 1); });
         }
 #pragma unroll 1
         for (int k = 0; k < cp.n_copies; ++k) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_copies_kernel(PlaneArgs
         {
             float S[16];
             load_tile_generic<uint8_t>(p, pl.pitch, es, S);
-            embed_prepare(S, em.scale, em.inv_scale, bp);
+            embed_prepare(S, em.scale, em.inv_scale, bp, [&]() { return flat_probe_global<uint8_t>(p, pl.pitch, es); });
         }
 #pragma unroll 1
         for (int k = 0; k < cp.n_copies; ++k) {

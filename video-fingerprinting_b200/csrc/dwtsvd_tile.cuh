@@ -45,6 +45,62 @@ inline unsigned every_mask(int payload_len) {
 }
 
 // ------------------------------------------------------------------------------------------
+// flat tiles on a quantisation boundary
+// ------------------------------------------------------------------------------------------
+// The kernels take sigma_0 from the exact 2x2 sums; the reference takes it from a float32 Haar band
+// whose taps are float32(1/sqrt(2)) (PyWavelets; oracle/haar.py), i.e. from LL values that are a few
+// 1e-8 (relative) below the exact ones.  That only matters where sigma_0 sits on a quantisation boundary
+// (k*scale for the floor, (k+1/2)*scale for the bit) - and there the reference is still deterministic
+// for FLAT tiles (all 64 samples equal v): LL = 4*fl(c*fl(c*v)) in every coefficient, cv2.dct and LAPACK
+// are exact on a constant block, so sigma_0 = 16*fl(c*fl(c*|v|)) (checked against the oracle for every
+// uint8 v and random float v in tests/test_oracle_golden.py).  E.g. a flat 255 tile has sigma_0 =
+// 2039.99988 (bit 1, floor 135), not 2040 (bit 0, floor 136); black 0/16 and white 235 are no boundary cases.
+// So: when sigma_0 lands within 2^-21 (relative) of a boundary - rare - the kernel probes whether the tile
+// is flat and, if so, takes the reference's value.  Non-flat tiles on a boundary stay what they are:
+// decided by float32 rounding inside cv2.dct / sgesdd, which no independent implementation reproduces.
+constexpr float kHaarTap = 0.70710677f;          // float32(1/sqrt(2))
+__device__ __forceinline__ float flat_sigma_ref(float sample) {
+    return 16.0f * __fmul_rn(kHaarTap, __fmul_rn(kHaarTap, fabsf(sample)));
+}
+template <bool kBitThreshold>                    // extract: floor and bit boundaries; embed: the floor only
+__device__ __forceinline__ bool on_boundary(float sigma, float rem, float scale) {
+    const float tol = sigma * 4.7683716e-7f;     // 2^-21 relative (0 for an all-zero block: never taken)
+    bool b = (rem < tol) | (scale - rem < tol);
+    if (kBitThreshold) b |= fabsf(rem - 0.5f * scale) < tol;
+    return b;
+}
+// Probes: the common sample value of a flat tile, NaN otherwise.  Out of line: they run once in a few
+// thousand tiles and must not cost the hot path registers.
+template <typename T>
+static __device__ __noinline__ float flat_probe_global(const uint8_t* p, unsigned pitch, int es) {
+    const float v0 = (float)*reinterpret_cast<const T*>(p);
+    bool flat = true;
+#pragma unroll 1
+    for (int y = 0; y < 8; ++y) {
+        const T* r = reinterpret_cast<const T*>(p + (unsigned long long)y * pitch);
+#pragma unroll 1
+        for (int x = 0; x < 8; ++x) flat &= ((float)r[x * es] == v0);
+    }
+    return flat ? v0 : __int_as_float(0x7FC00000);
+}
+static __device__ __noinline__ float flat_probe_shared(unsigned addr, unsigned pitch) {
+    unsigned w0;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(addr));
+    const unsigned want = __byte_perm(w0, 0u, 0x0000);
+    bool flat = true;
+#pragma unroll 1
+    for (int y = 0; y < 8; ++y) {
+        unsigned a, b;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr + y * pitch));
+        flat &= (a == want) & (b == want);
+    }
+    return flat ? (float)(w0 & 0xFFu) : __int_as_float(0x7FC00000);
+}
+struct NoProbe {     // callers whose input cannot be probed cheaply keep the exact-sum value
+    __device__ __forceinline__ float operator()() const { return __int_as_float(0x7FC00000); }
+};
+
+// ------------------------------------------------------------------------------------------
 // tile loaders: produce S[16] (2x2 sums, row-major over the 4x4 block)
 // ------------------------------------------------------------------------------------------
 // Fast path: planar uint8, 8-byte aligned rows.  rows[r] keeps the raw bytes for the embed.
@@ -118,9 +174,9 @@ __device__ __forceinline__ void load_tile_generic(const uint8_t* p, unsigned pit
 // Per-sample increment of each 2x2 of the tile for watermark bit `bit`: D[4*i+j] = (S'-S)[i][j]/4.
 // kStash: park S in shared memory while the eigen-iteration runs (4 STS.128 + 4 LDS.128 per
 // thread) instead of letting the compiler rebuild it from the pixel bytes under register pressure.
-template <bool kStash>
+template <bool kStash, typename Probe>
 __device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scale, float inv_scale,
-                                             float bias, float (&D)[16], float4* stash) {
+                                             float bias, float (&D)[16], float4* stash, Probe probe) {
     float v[4];
     bool zero;
     if (kStash) {
@@ -129,9 +185,16 @@ __device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scal
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)),
                          "f"(S[4 * i]), "f"(S[4 * i + 1]), "f"(S[4 * i + 2]), "f"(S[4 * i + 3]) : "memory");
     }
-    const float sigma = 0.5f * top_singular<true>(S, v, zero);   // sigma_0 of the LL block
+    float sigma = 0.5f * top_singular<true>(S, v, zero);   // sigma_0 of the LL block
     float q, rem;
     floor_divmod(sigma, scale, inv_scale, q, rem);
+    if (on_boundary<false>(sigma, rem, scale)) {
+        const float flat = probe();
+        if (flat == flat) {
+            sigma = flat_sigma_ref(flat);
+            floor_divmod(sigma, scale, inv_scale, q, rem);
+        }
+    }
     const float target = (q + 0.25f + 0.5f * (float)bit) * scale;
     if (zero) {
         // svd(0) = (I, 0, I): the reference puts sigma_0' on DCT coefficient [0][0], i.e. a flat
@@ -165,10 +228,18 @@ struct BlockPair {
     bool zero;
 };
 
-__device__ __forceinline__ void embed_prepare(const float (&S)[16], float scale, float inv_scale, BlockPair& bp) {
+template <typename Probe>
+__device__ __forceinline__ void embed_prepare(const float (&S)[16], float scale, float inv_scale, BlockPair& bp, Probe probe) {
     bp.sigma = 0.5f * top_singular<true>(S, bp.v, bp.zero);
     float rem;
     floor_divmod(bp.sigma, scale, inv_scale, bp.q, rem);
+    if (on_boundary<false>(bp.sigma, rem, scale)) {
+        const float flat = probe();
+        if (flat == flat) {
+            bp.sigma = flat_sigma_ref(flat);
+            floor_divmod(bp.sigma, scale, inv_scale, bp.q, rem);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         bp.sv[i] = fmaf(S[4 * i + 3], bp.v[3], fmaf(S[4 * i + 2], bp.v[2], fmaf(S[4 * i + 1], bp.v[1], S[4 * i] * bp.v[0])));
@@ -190,12 +261,20 @@ __device__ __forceinline__ void embed_copy_deltas(const BlockPair& bp, int bit, 
     }
 }
 
-__device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, float inv_scale, float& sigma) {
+template <typename Probe>
+__device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, float inv_scale, float& sigma, Probe probe) {
     float v[4];
     bool zero;
     sigma = 0.5f * top_singular<false>(S, v, zero);
     float q, rem;
     floor_divmod(sigma, scale, inv_scale, q, rem);
+    if (on_boundary<true>(sigma, rem, scale)) {
+        const float flat = probe();
+        if (flat == flat) {
+            sigma = flat_sigma_ref(flat);
+            floor_divmod(sigma, scale, inv_scale, q, rem);
+        }
+    }
     return rem > 0.5f * scale ? 1 : 0;
 }
 
@@ -233,24 +312,41 @@ __device__ __forceinline__ void sums_from_rows_x2(const uint2 (&ra)[8], const ui
 }
 
 // extract_bit() for both lanes: bit 0 = first tile, bit 1 = second tile
-__device__ __forceinline__ unsigned extract_bits_x2(const f2 (&S)[16], float scale, float inv_scale) {
+// probe(0) / probe(1): flat probe of the first / second tile
+template <typename Probe>
+__device__ __forceinline__ unsigned extract_bits_x2(const f2 (&S)[16], float scale, float inv_scale, Probe probe) {
     f2 v[4];
     const Pair2 p = top_singular_x2<false>(S, v);
-    const f2 sigma = mul2(bc2(0.5f), p.sigma0);
+    f2 sigma = mul2(bc2(0.5f), p.sigma0);
     f2 q, rem;
     floor_divmod2(sigma, scale, inv_scale, q, rem);
+    const bool edge_x = on_boundary<true>(sigma.x, rem.x, scale), edge_y = on_boundary<true>(sigma.y, rem.y, scale);
+    if (edge_x | edge_y) {
+        const float fx = edge_x ? probe(0) : __int_as_float(0x7FC00000), fy = edge_y ? probe(1) : __int_as_float(0x7FC00000);
+        if (fx == fx) sigma.x = flat_sigma_ref(fx);
+        if (fy == fy) sigma.y = flat_sigma_ref(fy);
+        floor_divmod2(sigma, scale, inv_scale, q, rem);
+    }
     const float half = 0.5f * scale;
     return (rem.x > half ? 1u : 0u) | (rem.y > half ? 2u : 0u);
 }
 
 // embed_deltas() for both lanes (bits: bit 0 = first tile, bit 1 = second tile)
+template <typename Probe>
 __device__ __forceinline__ void embed_deltas_x2(const f2 (&S)[16], unsigned bits, float scale, float inv_scale, float bias,
-                                                f2 (&D)[16]) {
+                                                f2 (&D)[16], Probe probe) {
     f2 v[4];
     const Pair2 p = top_singular_x2<true>(S, v);
-    const f2 sigma = mul2(bc2(0.5f), p.sigma0);
+    f2 sigma = mul2(bc2(0.5f), p.sigma0);
     f2 q, rem;
     floor_divmod2(sigma, scale, inv_scale, q, rem);
+    const bool edge_x = on_boundary<false>(sigma.x, rem.x, scale), edge_y = on_boundary<false>(sigma.y, rem.y, scale);
+    if (edge_x | edge_y) {
+        const float fx = edge_x ? probe(0) : __int_as_float(0x7FC00000), fy = edge_y ? probe(1) : __int_as_float(0x7FC00000);
+        if (fx == fx) sigma.x = flat_sigma_ref(fx);
+        if (fy == fy) sigma.y = flat_sigma_ref(fy);
+        floor_divmod2(sigma, scale, inv_scale, q, rem);
+    }
     const f2 bit = make_float2((float)(bits & 1u), (float)((bits >> 1) & 1u));
     const f2 target = mul2(add2(add2(q, bc2(0.25f)), mul2(bc2(0.5f), bit)), bc2(scale));
     const f2 diff = add2(target, neg2(sigma));

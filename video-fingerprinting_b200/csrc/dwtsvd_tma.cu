@@ -312,7 +312,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
                 }
                 sums_from_rows_x2(ra, rb, S);
             }
-            bits = extract_bits_x2(S, ex.scale, ex.inv_scale);
+            bits = extract_bits_x2(S, ex.scale, ex.inv_scale,
+                                   [&](int which) { return flat_probe_shared(slot + (which ? tp.off_hi : tp.off_lo), sp); });
         }
         const unsigned ballot_lo = __ballot_sync(0xFFFFFFFFu, tp.live_lo && (bits & 1u));
         const unsigned ballot_hi = __ballot_sync(0xFFFFFFFFu, tp.live_hi && (bits & 2u));
@@ -428,7 +429,8 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
                     }
                     sums_from_rows_x2(ra, rb, S);
                 }
-                embed_deltas_x2(S, mybits, em.scale, em.inv_scale, 12582912.0f, D);
+                embed_deltas_x2(S, mybits, em.scale, em.inv_scale, 12582912.0f, D,
+                                [&](int which) { return flat_probe_shared(which ? mine_hi : mine_lo, sp); });
             }
 #pragma unroll
             for (int i2 = 0; i2 < 4; ++i2) {

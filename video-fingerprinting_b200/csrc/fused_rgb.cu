@@ -27,6 +27,22 @@ __device__ __forceinline__ void px_to_yuv(float c0, float c1, float c2, float& y
     v = fmaf(c2 - y, 0.877f, 0.5f);
 }
 
+// Flat-tile probe (dwtsvd_tile.cuh) for packed rgb frames: all 64 pixels equal -> the value of YUV channel
+// `channel` of that colour, NaN otherwise.
+static __device__ __noinline__ float flat_probe_rgb(const uint8_t* p, unsigned pitch, int channel) {
+    const uint8_t c0 = p[0], c1 = p[1], c2 = p[2];
+    bool flat = true;
+#pragma unroll 1
+    for (int y = 0; y < 8; ++y) {
+        const uint8_t* r = p + (unsigned long long)y * pitch;
+#pragma unroll 1
+        for (int x = 0; x < 8; ++x) flat &= (r[3 * x] == c0) & (r[3 * x + 1] == c1) & (r[3 * x + 2] == c2);
+    }
+    float y, u, v;
+    px_to_yuv((float)c0, (float)c1, (float)c2, y, u, v);
+    return flat ? (channel == 0 ? y : (channel == 1 ? u : v)) : __int_as_float(0x7FC00000);
+}
+
 // bytes of one tile row: 8 pixels x 3 channels = 24 bytes = 6 words
 template <bool kAligned>
 __device__ __forceinline__ void load_row24(const uint8_t* p, unsigned (&w)[6]) {
@@ -97,7 +113,9 @@ __global__ void __launch_bounds__(128, 4) dwtsvd_embed_rgb8_kernel(RgbArgs a, Em
     float D[3][16];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
-        if (kMask & (1 << ch)) embed_deltas<false>(S[ch], bit, a.scale[ch], 1.0f / a.scale[ch], 0.0f, D[ch], nullptr);
+        if (kMask & (1 << ch))
+            embed_deltas<false>(S[ch], bit, a.scale[ch], 1.0f / a.scale[ch], 0.0f, D[ch], nullptr,
+                                [&]() { return flat_probe_rgb(a.src + off, a.pitch, ch); });
 
     // Pass B: convert again, add the increments in YUV space, convert back, clip, round, store.
 #pragma unroll
@@ -164,7 +182,7 @@ __global__ void __launch_bounds__(128) dwtsvd_extract_rgb8_kernel(RgbArgs a, int
             }
         }
         float sigma;
-        bit = extract_bit(S, ex.scale, ex.inv_scale, sigma);
+        bit = extract_bit(S, ex.scale, ex.inv_scale, sigma, [&]() { return flat_probe_rgb(a.src + off, a.pitch, channel); });
     }
     const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
     const unsigned lane = threadIdx.x & 31;

@@ -157,6 +157,9 @@ int mark_host(const uint8_t* src, uint8_t* dst, const b200wm_plane* pl, const ui
     int rc = check_host_plane(pl);
     if (rc) return rc;
     if (!src || !dst || !wm_host || n_rows <= 0 || wm_words <= 0) return B200WM_ERR_INVALID;
+    if (frame_row_host)
+        for (int f = 0; f < pl->n_frames; ++f)
+            if (frame_row_host[f] < 0 || frame_row_host[f] >= n_rows) return B200WM_ERR_INVALID;
     if (pl->n_frames == 0) return B200WM_OK;
     const int chunk = pick_chunk(chunk_frames, pl);
     const size_t plane = (size_t)pl->width * pl->height;
@@ -256,6 +259,85 @@ int detect_host(const uint8_t* src, const b200wm_plane* pl, float scale, int pay
         } else {
             B200WM_CUDA_TRY(cudaEventRecord(c->drained[s], c->run));
         }
+    }
+    B200WM_CUDA_TRY(cudaMemcpyAsync(patterns_host, c->pat.p, (size_t)pl->n_frames * payload_len, cudaMemcpyDeviceToHost, c->run));
+    if (pos_counts_host)
+        B200WM_CUDA_TRY(cudaMemcpyAsync(pos_counts_host, c->cnt.p, sizeof(int32_t) * (size_t)pl->n_frames * payload_len,
+                                        cudaMemcpyDeviceToHost, c->run));
+    return B200WM_OK;
+    }();
+    const int rc_sync = c->sync_all();
+    return rc ? rc : rc_sync;
+}
+
+// Mark and verify in one pass over the link: upload a chunk, embed in place, extract + per-frame vote from the
+// marked chunk while it is still resident, download the marked planes.  This is the reference's own "watermark,
+// then always verify" step (tests/mark_video_to_hls.py:356-399 re-reads every marked segment through
+// detect_patterns_in_segment, :253-266; tests/segment_mark_detect_hls.py:195-243 does the same per segment) with
+// 2*W*H bytes per frame on the link instead of the 3*W*H of mark_host + detect_host.
+int mark_verify_host(const uint8_t* src, uint8_t* dst, const b200wm_plane* pl, const uint32_t* wm_host, int n_rows, int wm_words,
+                     long long wm_len, const int32_t* frame_row_host, float scale, int payload_len, const int32_t* perm_host,
+                     uint8_t* patterns_host, uint32_t* raw_bits_host, int32_t* pos_counts_host, int chunk_frames) {
+    int rc = check_host_plane(pl);
+    if (rc) return rc;
+    if (!src || !dst || !wm_host || n_rows <= 0 || wm_words <= 0 || !perm_host || !patterns_host || payload_len <= 0)
+        return B200WM_ERR_INVALID;
+    if (frame_row_host)
+        for (int f = 0; f < pl->n_frames; ++f)
+            if (frame_row_host[f] < 0 || frame_row_host[f] >= n_rows) return B200WM_ERR_INVALID;
+    if (pl->n_frames == 0) return B200WM_OK;
+    const int chunk = pick_chunk(chunk_frames, pl);
+    const size_t plane = (size_t)pl->width * pl->height;
+    const TileGeom g = make_geom(pl->height, pl->width);
+    const size_t words = g.words ? g.words : 1;
+    HostCtx* c = nullptr;
+    if ((rc = current_ctx(&c))) return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if ((rc = c->init())) return rc;
+    for (int i = 0; i < kSlots; ++i) {
+        if ((rc = c->buf[i].reserve(plane * chunk))) return rc;
+        if ((rc = c->raw[i].reserve(sizeof(uint32_t) * (size_t)chunk * words))) return rc;
+    }
+    if ((rc = c->wm.reserve(sizeof(uint32_t) * (size_t)n_rows * wm_words))) return rc;
+    if ((rc = c->pat.reserve((size_t)pl->n_frames * payload_len))) return rc;
+    if ((rc = c->cnt.reserve(sizeof(int32_t) * (size_t)pl->n_frames * payload_len))) return rc;
+    if ((rc = c->perm.reserve(sizeof(int32_t) * (size_t)payload_len))) return rc;
+    B200WM_CUDA_TRY(cudaMemcpyAsync(c->wm.p, wm_host, sizeof(uint32_t) * (size_t)n_rows * wm_words, cudaMemcpyHostToDevice, c->run));
+    B200WM_CUDA_TRY(cudaMemcpyAsync(c->perm.p, perm_host, sizeof(int32_t) * (size_t)payload_len, cudaMemcpyHostToDevice, c->run));
+    if (frame_row_host) {
+        if ((rc = c->rows.reserve(sizeof(int32_t) * (size_t)pl->n_frames))) return rc;
+        B200WM_CUDA_TRY(cudaMemcpyAsync(c->rows.p, frame_row_host, sizeof(int32_t) * (size_t)pl->n_frames, cudaMemcpyHostToDevice, c->run));
+    }
+    rc = [&]() -> int {
+    int rc = B200WM_OK;
+    int k = 0;
+    for (int f0 = 0; f0 < pl->n_frames; f0 += chunk, ++k) {
+        const int m = pl->n_frames - f0 < chunk ? pl->n_frames - f0 : chunk;
+        const int s = k % kSlots;
+        uint8_t* buf = (uint8_t*)c->buf[s].p;
+        uint32_t* raw = (uint32_t*)c->raw[s].p;
+        int32_t* cnt = (int32_t*)c->cnt.p + (size_t)f0 * payload_len;
+        uint8_t* pat = (uint8_t*)c->pat.p + (size_t)f0 * payload_len;
+        b200wm_plane host = *pl, devp = *pl;
+        host.n_frames = devp.n_frames = m;
+        devp.pitch_bytes = pl->width;
+        devp.frame_stride_bytes = (long long)plane;
+        if (k >= kSlots) B200WM_CUDA_TRY(cudaStreamWaitEvent(c->up, c->drained[s], 0));     // the slot's previous chunk is back on the host
+        if ((rc = copy_planes(buf, src + (size_t)f0 * pl->frame_stride_bytes, &host, m, true, c->up))) return rc;
+        B200WM_CUDA_TRY(cudaEventRecord(c->uploaded[s], c->up));
+        B200WM_CUDA_TRY(cudaStreamWaitEvent(c->run, c->uploaded[s], 0));
+        if ((rc = launch_dwtsvd_embed(buf, buf, &devp, (const uint32_t*)c->wm.p, wm_words, wm_len,
+                                      frame_row_host ? (const int32_t*)c->rows.p + f0 : nullptr, scale, c->run)))
+            return rc;
+        if ((rc = launch_dwtsvd_extract(buf, &devp, scale, raw, g.words, payload_len, cnt, nullptr, c->run))) return rc;
+        if ((rc = launch_vote_finish(cnt, m, payload_len, g.block_num, (const int32_t*)c->perm.p, pat, nullptr, c->run))) return rc;
+        B200WM_CUDA_TRY(cudaEventRecord(c->computed[s], c->run));
+        B200WM_CUDA_TRY(cudaStreamWaitEvent(c->down, c->computed[s], 0));
+        if ((rc = copy_planes(dst + (size_t)f0 * pl->frame_stride_bytes, buf, &host, m, false, c->down))) return rc;
+        if (raw_bits_host && g.words)
+            B200WM_CUDA_TRY(cudaMemcpyAsync(raw_bits_host + (size_t)f0 * g.words, raw, sizeof(uint32_t) * (size_t)m * g.words,
+                                            cudaMemcpyDeviceToHost, c->down));
+        B200WM_CUDA_TRY(cudaEventRecord(c->drained[s], c->down));
     }
     B200WM_CUDA_TRY(cudaMemcpyAsync(patterns_host, c->pat.p, (size_t)pl->n_frames * payload_len, cudaMemcpyDeviceToHost, c->run));
     if (pos_counts_host)
