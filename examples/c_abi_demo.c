@@ -55,7 +55,7 @@ int main(void) {
     pl.dtype = B200WM_U8; pl.n_frames = 1; pl.height = h; pl.width = w;
     pl.pitch_bytes = w; pl.frame_stride_bytes = (int64_t)h * w; pl.elem_stride = 1;
 
-    CHECK_WM(b200wm_dwtsvd_embed(d_plane, d_plane, &pl, d_wm, words, block_num, NULL, 15.0f, NULL));
+    CHECK_WM(b200wm_dwtsvd_embed(d_plane, d_plane, &pl, d_wm, 1, words, block_num, NULL, 15.0f, NULL));
     CHECK_WM(b200wm_dwtsvd_extract(d_plane, &pl, 15.0f, d_raw, words, payload_len, d_counts, NULL));
     CHECK_WM(b200wm_vote_finish(d_counts, 1, payload_len, block_num, d_perm, d_patterns, NULL, NULL));
     CHECK_CUDA(cudaDeviceSynchronize());

@@ -118,10 +118,12 @@ B200WM_API int32_t b200wm_words_per_frame(int height, int width);
  * reference rounds sample + increment, which differs by 1 LSB only when an increment is exactly
  * k + 0.5 (observed on 4e-6 of the samples).  F32 planes are written unrounded.
  * wm_packed: [n_wm_rows, wm_words] packed bits; frame f uses row
- * frame_wm_row[f] (NULL -> row 0 for every frame).  wm_len = bits per row.
+ * frame_wm_row[f] (NULL -> row 0 for every frame; entries are clamped into [0, n_wm_rows) on the device, so a
+ * bad table can never read outside wm_packed - validate tables on the host if a wrong row must be an error).
+ * wm_len = bits per row.
  */
 B200WM_API int b200wm_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* plane,
-                        const uint32_t* wm_packed, int32_t wm_words, int64_t wm_len,
+                        const uint32_t* wm_packed, int32_t n_wm_rows, int32_t wm_words, int64_t wm_len,
                         const int32_t* frame_wm_row, float scale, void* stream);
 
 /*
@@ -178,7 +180,7 @@ B200WM_API int b200wm_dct8_masks(const void* lum, const b200wm_plane* lum_plane,
  */
 B200WM_API int b200wm_dct8_embed(const void* src, void* dst, const b200wm_plane* plane,
                       const float* block_mean, const float* tex_mask, const double* frame_sum,
-                      const uint32_t* wm_packed, int32_t wm_words, int64_t wm_len,
+                      const uint32_t* wm_packed, int32_t n_wm_rows, int32_t wm_words, int64_t wm_len,
                       const int32_t* frame_wm_row, float alpha, void* stream);
 /* Replaces the block loop of DctDecoder.decode (extract/dct_decoder.py:17-27). */
 B200WM_API int b200wm_dct8_extract(const void* src, const b200wm_plane* plane,
@@ -241,7 +243,7 @@ B200WM_API int b200wm_yuv32_to_bgr8(const float* yuv, uint8_t* bgr, int64_t n_pi
  */
 B200WM_API int b200wm_dwtsvd_embed_rgb8(const uint8_t* src, uint8_t* dst, int32_t n_frames, int32_t height, int32_t width,
                             int64_t pitch_bytes, int64_t frame_stride_bytes, const float* scales, const uint32_t* wm_packed,
-                            int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, void* stream);
+                            int32_t n_wm_rows, int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, void* stream);
 /*
  * Extractor.__check_frame's conversion + DwtDctSvdDecoder.decode on YUV channel `channel`
  * (video/extractor.py:30-33, extract/dwt_dct_svd_decoder.py:12-37) in one kernel.  Outputs as

@@ -45,7 +45,8 @@ def test_extractor_tracks_reference_under_attack(marked_frames, name, attack):
         raw, counts = ops.dwtsvd_extract(torch.from_numpy(attacked).to(DEV), payload_len=8)
         got = ops.unpack_bits(raw, n)[0]
         diff = np.flatnonzero(got != want)
-        edge, _, _ = knife_edge_blocks(attacked.astype(np.float32))
+        edge, _, _ = knife_edge_blocks(attacked.astype(np.float32), check=False)
+        assert edge.mean() < (3e-3 if name.startswith("jpeg") else 1e-3), (name, edge.mean())     # requantised planes: see below
         assert all(edge[c] for c in diff), f"{name}: raw bits differ away from quantisation boundaries"
         assert diff.size <= 0.002 * n
         ber_ref = float((want != wm).mean())
@@ -73,18 +74,39 @@ def test_gpu_attack_kernels_match_cpu_definitions(marked_frames):
     t = torch.from_numpy(marked.copy()).to(DEV)
     ops.attack_add_noise_(t, torch.from_numpy(noise).to(DEV))
     assert np.array_equal(t.cpu().numpy(), want)
+    from scipy.fft import dctn, idctn
     for q in (95, 75, 50):
         want = attacks.jpeg_requant(marked[0], q)
         t = torch.from_numpy(marked[:1].copy()).to(DEV)
         ops.attack_jpeg_requant_(t, q)
         got = t.cpu().numpy()[0]
         d = np.abs(got.astype(np.int16) - want)
-        assert (d > 0).mean() < 0.05 and d.max() <= 8, (q, (d > 0).mean(), d.max())
-        # and the two extractors agree on what is left of the mark after the GPU attack
+        # Every block that differs must be EXPLAINED by a rounding tie, checked against an exact (float64) DCT:
+        #  (a) a coefficient whose c/Q lies within 1e-4 of k + 1/2 (np.rint may go either way on float32 noise), or
+        #  (b) identical quantised coefficients, and the differing samples are 1 level apart with an exact value
+        #      within 1e-3 of k + 1/2 before the final rounding.
+        table = attacks.jpeg_table(q).astype(np.float64)
+        bad = np.argwhere(d.reshape(H // 8, 8, W // 8, 8).max(axis=(1, 3)) > 0)
+        coeff_ties = round_ties = 0
+        for by, bx in bad:
+            blk = marked[0, by * 8:by * 8 + 8, bx * 8:bx * 8 + 8].astype(np.float64) - 128.0
+            ratio = dctn(blk, norm="ortho") / table
+            if (0.5 - np.abs(ratio - np.rint(ratio))).min() < 1e-4:
+                coeff_ties += 1
+                continue
+            exact = idctn(np.rint(ratio) * table, norm="ortho") + 128.0
+            dd = d[by * 8:by * 8 + 8, bx * 8:bx * 8 + 8]
+            assert dd.max() == 1 and (np.abs(np.abs(exact - np.floor(exact)) - 0.5)[dd > 0] < 1e-3).all(), (q, by, bx)
+            round_ties += 1
+        print(f"jpeg q{q}: {len(bad)} of {H * W // 64} blocks differ: {coeff_ties} coefficient ties, {round_ties} final-rounding ties")
+        assert len(bad) < 0.08 * (H * W // 64)
+        # and the two extractors agree on what is left of the mark after the GPU attack; requantised planes sit on
+        # quantisation boundaries more often than camera content (sums of few lattice coefficients), hence the limit
         raw, _ = ops.dwtsvd_extract(t)
         bits = ops.unpack_bits(raw, H * W // 64)[0]
         ref_bits = o_svd.extract_plane(got)[0]
-        edge, _, _ = knife_edge_blocks(got.astype(np.float32))
+        edge, _, _ = knife_edge_blocks(got.astype(np.float32), check=False)
+        assert edge.mean() < 3e-3, edge.mean()
         assert all(edge[c] for c in np.flatnonzero(bits != ref_bits))
 
 

@@ -238,3 +238,125 @@ def test_fingerprint_layer_copy_sequence_roundtrip():
     other = {k: v for k, v in payloads.items() if k.endswith("_1")}
     partial = fp.detect_segment_copies(stream, frame_seg, segment_payloads=other)
     assert [r["detected_copy_index"] for r in partial] == [None, None, 1, None]
+
+
+def test_mark_verify_host_equals_mark_then_detect():
+    """b200wm_dwtsvd_mark_verify_host (one upload, embed, extract + vote on the resident marked chunk, one download:
+    the reference's mark-then-verify step, tests/mark_video_to_hls.py:356-399) returns the very bytes of
+    b200wm_dwtsvd_mark_host and the very patterns / raw bits of b200wm_dwtsvd_detect_host on them."""
+    from b200wm import ops
+    from oracle import synth
+    n, h, w = 9, 240, 320
+    planes = np.stack([synth.luma_plane_u8(h, w, f, 19) for f in range(n)])
+    payloads = [o_pay.payload_for_segment(s) for s in (9, 100, 201)]
+    rows = np.stack([o_pay.generate_wm(p, (1, h * w // 64), KEY)[0] for p in payloads])
+    frame_row = np.array([0, 0, 0, 1, 1, 1, 2, 2, 2], dtype=np.int32)
+    src = torch.from_numpy(planes).pin_memory()
+    perm = o_pay.permutation(8, KEY)
+    for chunk in (0, 1, 4):
+        two_a, one = torch.empty_like(src), torch.empty_like(src)
+        ops.dwtsvd_mark_host(src, two_a, rows, frame_wm_row=frame_row, chunk_frames=chunk)
+        pat_two, raw_two = ops.dwtsvd_detect_host(two_a, perm, chunk_frames=chunk, want_raw_bits=True)
+        pat_one, raw_one = ops.dwtsvd_mark_verify_host(src, one, rows, perm, frame_wm_row=frame_row, chunk_frames=chunk,
+                                                       want_raw_bits=True)
+        assert np.array_equal(one.numpy(), two_a.numpy())
+        assert np.array_equal(pat_one, pat_two) and np.array_equal(raw_one, raw_two)
+        for f in range(n):
+            assert np.array_equal(pat_one[f], payloads[frame_row[f]])
+    # against the oracle on one frame
+    want = o_svd.embed_plane_u8(planes[4], rows[1])
+    assert np.abs(one.numpy()[4].astype(np.int16) - want).max() <= 1
+    with pytest.raises(ValueError):                 # a row index outside the table is an error on the host path
+        ops.dwtsvd_mark_verify_host(src, one, rows, perm, frame_wm_row=np.full(n, 3, dtype=np.int32))
+    with pytest.raises(ValueError):
+        ops.dwtsvd_mark_host(src, one, rows, frame_wm_row=np.full(n, -1, dtype=np.int32))
+
+
+def test_degenerate_votes_on_the_array_it_is_given():
+    """The reference's DeShuffler.degenerate works on whatever array it receives (de_shuffler.py:14-22): an inverted,
+    sliced or edited copy of decode()'s result must give the vote of THAT array, not of the decoder's cached bits."""
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.extract.dwt_dct_svd_decoder import DwtDctSvdDecoder
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.degenerator.de_shuffler import DeShuffler
+    from oracle import synth
+    yuv = bracket.to_yuv(synth.random_bgr(240, 320, 5))
+    enc = DwtDctSvdEncoder()
+    enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(yuv.shape)))
+    enc.encode(yuv)
+    bits = DwtDctSvdDecoder().decode(yuv)
+    assert type(bits) is np.ndarray and bits.dtype == np.float64
+    deg = DeShuffler(key=KEY).set_shape(PAYLOAD.shape)
+    assert np.array_equal(deg.degenerate(bits), PAYLOAD)
+    assert np.array_equal(deg.degenerate(1 - bits), 1 - PAYLOAD)
+    assert np.array_equal(deg.degenerate(1 - bits), o_pay.degenerate(1 - bits, 8, KEY))
+    half = bits[:, :bits.shape[1] // 2 // 8 * 8]
+    assert np.array_equal(deg.degenerate(half), o_pay.degenerate(half, 8, KEY))
+    edited = bits.copy()
+    edited[0, 6::8] = 1 - edited[0, 6::8]           # position 6 -> payload index perm[6]
+    want = o_pay.degenerate(edited, 8, KEY)
+    assert not np.array_equal(want, PAYLOAD) and np.array_equal(deg.degenerate(edited), want)
+    bits[0, 6::8] = 1 - bits[0, 6::8]               # the same edit in place
+    assert np.array_equal(deg.degenerate(bits), want)
+
+
+def test_extractor_batched_mode_with_degrayscale_formats_like_per_frame_mode():
+    """Extractor(batch_frames=N) with a DeGrayScale degenerator logs the 0/255 image of payload_shape that the
+    per-frame path (and the reference, de_grayscale.py:15-23) returns, not flat 0/1 vectors."""
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.extract.dwt_dct_svd_decoder import DwtDctSvdDecoder
+    from offmark_b200.generator.grayscale import GrayScale
+    from offmark_b200.degenerator.de_grayscale import DeGrayScale
+    from offmark_b200.video.embedder import Embedder
+    from offmark_b200.video.extractor import Extractor
+    from offmark_b200.video.memory_io import ArrayReader, ArrayWriter
+    from oracle import synth
+    img = (np.random.RandomState(5).rand(4, 4) > 0.5).astype(np.uint8) * 255
+    frames = [synth.random_bgr(240, 320, s) for s in range(5)]
+    enc = DwtDctSvdEncoder()
+    enc.read_wm(GrayScale(key=KEY).generate_wm(img, enc.wm_capacity(frames[0].shape)))
+    w = ArrayWriter()
+    Embedder(ArrayReader(frames), enc, w, batch_frames=2).start()
+
+    def run(batch):
+        ex = Extractor(ArrayReader(w.frames), DwtDctSvdDecoder(), DeGrayScale(key=KEY).set_shape(img.shape), batch_frames=batch)
+        ex.start()
+        return ex.patterns
+    one, many = run(1), run(4)
+    assert len(one) == len(many) == len(frames)
+    for a, b in zip(one, many):
+        assert a.shape == img.shape == b.shape and a.dtype == b.dtype == np.uint8
+        assert np.array_equal(a, b) and np.array_equal(a, img)
+
+
+def test_argument_checks_of_the_wrappers():
+    """a CPU watermark tensor or an out-of-range row must be a ValueError, never a device fault; planes
+    with a dimension below 8 have raw-bit words but no tile."""
+    from b200wm import ops
+    dev = torch.device("cuda:0")
+    frames = torch.zeros((2, 64, 64, 3), dtype=torch.uint8, device=dev)
+    planes = torch.zeros((2, 64, 64), dtype=torch.uint8, device=dev)
+    packed_cpu, n = ops.pack_bits(np.zeros((2, 64), dtype=np.int64))
+    packed, _ = ops.pack_bits(np.zeros((2, 64), dtype=np.int64), device=dev)
+    masks = ops.dct8_masks(planes)
+    for call in (lambda wm, **k: ops.dwtsvd_embed_rgb8_(frames, wm, n, **k),
+                 lambda wm, **k: ops.dct8_embed_(planes, masks, wm, n, **k),
+                 lambda wm, **k: ops.dwtsvd_embed_(planes, wm, n, **k)):
+        with pytest.raises(ValueError):
+            call(packed_cpu)
+        with pytest.raises(ValueError):
+            call(packed.to(torch.int64))
+        bad = torch.tensor([0, 2], dtype=torch.int32, device=dev)
+        with pytest.raises(ValueError):
+            call(packed, frame_wm_row=bad, validate_rows=True)
+        call(packed, frame_wm_row=bad)                       # unvalidated: the device clamps the row, no fault
+        torch.cuda.synchronize()
+    for h, w in ((4, 64), (64, 4), (4, 512)):
+        t = torch.full((3, h, w), 200, dtype=torch.uint8, device=dev)
+        for path in (0, 1):
+            ops.set_path(path)
+            raw, counts = ops.dwtsvd_extract(t, payload_len=8)
+            assert raw.shape == (3, (h * w // 64 + 31) // 32)
+            assert not raw.any().item() and not counts.any().item()
+        ops.set_path(0)
+    torch.cuda.synchronize()

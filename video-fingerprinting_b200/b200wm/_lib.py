@@ -37,20 +37,20 @@ PROTOTYPES = {
     "b200wm_block_num": (_i64, [C.c_int, C.c_int]),
     "b200wm_tile_count": (_i64, [C.c_int, C.c_int]),
     "b200wm_words_per_frame": (_i32, [C.c_int, C.c_int]),
-    "b200wm_dwtsvd_embed": (C.c_int, [_vp, _vp, _PP, _vp, _i32, _i64, _vp, _f32, _vp]),
+    "b200wm_dwtsvd_embed": (C.c_int, [_vp, _vp, _PP, _vp, _i32, _i32, _i64, _vp, _f32, _vp]),
     "b200wm_dwtsvd_embed_copies": (C.c_int, [_vp, _PP, _vp, _i64, _i32, _vp, _i32, _i32, _i64, _vp, _f32, _vp]),
     "b200wm_dwtsvd_extract": (C.c_int, [_vp, _PP, _f32, _vp, _i32, _i32, _vp, _vp]),
     "b200wm_dwtsvd_sigma": (C.c_int, [_vp, _PP, _vp, _vp]),
     "b200wm_dwtsvd_sigma_dct": (C.c_int, [_vp, _PP, _vp, _vp]),
     "b200wm_dct8_masks": (C.c_int, [_vp, _PP, _vp, _vp, _vp, _vp]),
-    "b200wm_dct8_embed": (C.c_int, [_vp, _vp, _PP, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _f32, _vp]),
+    "b200wm_dct8_embed": (C.c_int, [_vp, _vp, _PP, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _f32, _vp]),
     "b200wm_dct8_extract": (C.c_int, [_vp, _PP, _vp, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp]),
     "b200wm_vote_counts": (C.c_int, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "b200wm_vote_finish": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b200wm_pattern_hist": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "b200wm_bgr8_to_yuv32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "b200wm_yuv32_to_bgr8": (C.c_int, [_vp, _vp, _i64, _vp]),
-    "b200wm_dwtsvd_embed_rgb8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _i32, _i64, _vp, _vp]),
+    "b200wm_dwtsvd_embed_rgb8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
     "b200wm_dwtsvd_extract_rgb8": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),
     "b200wm_dwtsvd_mark_host": (C.c_int, [_vp, _vp, _PP, _vp, _i32, _i32, _i64, _vp, _f32, _i32]),
     "b200wm_dwtsvd_detect_host": (C.c_int, [_vp, _PP, _f32, _i32, _vp, _vp, _vp, _vp, _i32]),

@@ -12,6 +12,7 @@ Tensor conventions
   packed bits int32 tensors holding little-endian uint32 bit words (bit c -> word c>>5, bit c&31).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -20,6 +21,7 @@ from . import _lib
 from ._lib import lib, check, Plane
 
 _ESIZE = {torch.uint8: (1, _lib.U8), torch.float32: (4, _lib.F32)}
+_VALIDATE = os.environ.get("B200WM_VALIDATE", "0") not in ("", "0")
 
 
 def require_cuda():
@@ -130,8 +132,25 @@ def unpack_bits(raw_bits, n):
     return np.unpackbits(a, axis=1, bitorder="little")[:, :n]
 
 
+def _check_wm(wm_packed, frame_wm_row, n_frames, validate_rows):
+    """The packed watermark table and the per-frame row table must be what the kernels dereference: contiguous
+    CUDA int32.  Row values are clamped on the device (never an out-of-bounds read); ``validate_rows`` (or
+    B200WM_VALIDATE=1) additionally checks them here, at the price of a device synchronisation."""
+    if not isinstance(wm_packed, torch.Tensor) or wm_packed.dtype != torch.int32 or wm_packed.dim() != 2 \
+            or not wm_packed.is_contiguous() or not wm_packed.is_cuda:
+        raise ValueError("wm_packed must be a contiguous CUDA int32 [rows, words] tensor (see pack_bits)")
+    if frame_wm_row is not None:
+        if not isinstance(frame_wm_row, torch.Tensor) or frame_wm_row.dtype != torch.int32 or frame_wm_row.numel() != n_frames \
+                or not frame_wm_row.is_cuda or not frame_wm_row.is_contiguous():
+            raise ValueError("frame_wm_row must be a contiguous CUDA int32 [n_frames] tensor")
+        if (validate_rows or _VALIDATE) and frame_wm_row.numel():
+            lo, hi = int(frame_wm_row.min()), int(frame_wm_row.max())
+            if lo < 0 or hi >= wm_packed.shape[0]:
+                raise ValueError(f"frame_wm_row holds rows {lo}..{hi} but wm_packed has {wm_packed.shape[0]} rows")
+
+
 # ----------------------------------------------------------------------------- DWT / SVD pair
-def dwtsvd_embed_(planes, wm_packed, wm_len, scale=15.0, channel=None, frame_wm_row=None, out=None):
+def dwtsvd_embed_(planes, wm_packed, wm_len, scale=15.0, channel=None, frame_wm_row=None, out=None, validate_rows=False):
     """In-place (or into ``out``, same geometry, pre-filled) embed.  Returns the written tensor."""
     require_cuda()
     v, pl = describe(planes, channel)
@@ -140,13 +159,9 @@ def dwtsvd_embed_(planes, wm_packed, wm_len, scale=15.0, channel=None, frame_wm_
     if (dpl.pitch_bytes, dpl.frame_stride_bytes, dpl.elem_stride, dpl.height, dpl.width, dpl.n_frames, dpl.dtype) != \
             (pl.pitch_bytes, pl.frame_stride_bytes, pl.elem_stride, pl.height, pl.width, pl.n_frames, pl.dtype):
         raise ValueError("out must have the geometry of planes")
-    if wm_packed.dtype != torch.int32 or wm_packed.dim() != 2 or not wm_packed.is_contiguous() or not wm_packed.is_cuda:
-        raise ValueError("wm_packed must be a contiguous CUDA int32 [rows, words] tensor (see pack_bits)")
-    if frame_wm_row is not None and (frame_wm_row.dtype != torch.int32 or frame_wm_row.numel() != pl.n_frames
-                                     or not frame_wm_row.is_cuda or not frame_wm_row.is_contiguous()):
-        raise ValueError("frame_wm_row must be a contiguous CUDA int32 [n_frames] tensor")
-    check(lib.b200wm_dwtsvd_embed(_ptr(v), _ptr(dv), C.byref(pl), _ptr(wm_packed), wm_packed.shape[1], int(wm_len),
-                                  _ptr(frame_wm_row), float(scale), _stream()))
+    _check_wm(wm_packed, frame_wm_row, pl.n_frames, validate_rows)
+    check(lib.b200wm_dwtsvd_embed(_ptr(v), _ptr(dv), C.byref(pl), _ptr(wm_packed), wm_packed.shape[0], wm_packed.shape[1],
+                                  int(wm_len), _ptr(frame_wm_row), float(scale), _stream()))
     return dst_t
 
 
@@ -235,12 +250,13 @@ def dct8_masks(lum, channel=None):
     return block_mean, tex, frame_sum
 
 
-def dct8_embed_(planes, masks, wm_packed, wm_len, alpha=20.0, channel=None, frame_wm_row=None):
+def dct8_embed_(planes, masks, wm_packed, wm_len, alpha=20.0, channel=None, frame_wm_row=None, validate_rows=False):
     require_cuda()
     v, pl = describe(planes, channel)
     block_mean, tex, frame_sum = masks
+    _check_wm(wm_packed, frame_wm_row, pl.n_frames, validate_rows)
     check(lib.b200wm_dct8_embed(_ptr(v), _ptr(v), C.byref(pl), _ptr(block_mean), _ptr(tex), _ptr(frame_sum),
-                                _ptr(wm_packed), wm_packed.shape[1], int(wm_len), _ptr(frame_wm_row),
+                                _ptr(wm_packed), wm_packed.shape[0], wm_packed.shape[1], int(wm_len), _ptr(frame_wm_row),
                                 float(alpha), _stream()))
     return planes
 
@@ -335,14 +351,15 @@ def _rgb_frames(frames):
     return f, n, h, w, f.stride(1), (f.stride(0) if n > 1 else 0)
 
 
-def dwtsvd_embed_rgb8_(frames, wm_packed, wm_len, scales=(0.0, 15.0, 0.0), frame_wm_row=None):
+def dwtsvd_embed_rgb8_(frames, wm_packed, wm_len, scales=(0.0, 15.0, 0.0), frame_wm_row=None, validate_rows=False):
     """uint8 [N, H, W, 3] frames marked in place: colour conversion, DWT/SVD embed on the channels
     with a positive scale and conversion back, in one kernel (video/embedder.py:33-39)."""
     require_cuda()
     f, n, h, w, pitch, fstride = _rgb_frames(frames)
     sc = (C.c_float * 3)(*[float(s) for s in scales])
-    check(lib.b200wm_dwtsvd_embed_rgb8(_ptr(f), _ptr(f), n, h, w, pitch, fstride, sc, _ptr(wm_packed), wm_packed.shape[1],
-                                       int(wm_len), _ptr(frame_wm_row), _stream()))
+    _check_wm(wm_packed, frame_wm_row, n, validate_rows)
+    check(lib.b200wm_dwtsvd_embed_rgb8(_ptr(f), _ptr(f), n, h, w, pitch, fstride, sc, _ptr(wm_packed), wm_packed.shape[0],
+                                       wm_packed.shape[1], int(wm_len), _ptr(frame_wm_row), _stream()))
     return frames
 
 

@@ -14,7 +14,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int launch_dwtsvd_embed(const void*, void*, const b200wm_plane*, const uint32_t*, int, long long, const int32_t*, float,
+int launch_dwtsvd_embed(const void*, void*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float,
                         cudaStream_t);
 int launch_dwtsvd_extract(const void*, const b200wm_plane*, float, uint32_t*, int, int, int32_t*, float*, cudaStream_t);
 int launch_vote_counts(const uint32_t*, int, int, long long, int, int32_t*, cudaStream_t);
@@ -23,7 +23,7 @@ int launch_pattern_hist(const uint64_t*, const int32_t*, const int32_t*, int, in
                         int32_t*, cudaStream_t);
 int launch_dct8_masks(const void*, const b200wm_plane*, float*, float*, double*, cudaStream_t);
 int launch_dct8_embed(const void*, void*, const b200wm_plane*, const float*, const float*, const double*, const uint32_t*,
-                      int, long long, const int32_t*, float, cudaStream_t);
+                      int, int, long long, const int32_t*, float, cudaStream_t);
 int launch_dct8_extract(const void*, const b200wm_plane*, const float*, const float*, const double*, float, uint32_t*, int,
                         int, int32_t*, cudaStream_t);
 int launch_bgr8_to_yuv32(const uint8_t*, float*, long long, cudaStream_t);
@@ -32,7 +32,7 @@ int launch_dwtsvd_embed_copies(const void*, const b200wm_plane*, void*, long lon
                                const int32_t*, float, cudaStream_t);
 int launch_attack_noise(const void*, void*, const b200wm_plane*, const float*, cudaStream_t);
 int launch_attack_resize(const void*, const b200wm_plane*, void*, const b200wm_plane*, int, cudaStream_t);
-int launch_embed_rgb8(const uint8_t*, uint8_t*, int, int, int, long long, long long, const float*, const uint32_t*, int, long long,
+int launch_embed_rgb8(const uint8_t*, uint8_t*, int, int, int, long long, long long, const float*, const uint32_t*, int, int, long long,
                       const int32_t*, cudaStream_t);
 int launch_extract_rgb8(const uint8_t*, int, int, int, long long, long long, int, float, uint32_t*, int, int, int32_t*, cudaStream_t);
 int mark_host(const uint8_t*, uint8_t*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float, int);
@@ -97,8 +97,8 @@ B200WM_API int32_t b200wm_words_per_frame(int height, int width) {
 }
 
 B200WM_API int b200wm_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* plane, const uint32_t* wm_packed,
-                        int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, float scale, void* stream) {
-    return launch_dwtsvd_embed(src, dst, plane, wm_packed, wm_words, wm_len, frame_wm_row, scale, (cudaStream_t)stream);
+                        int32_t n_wm_rows, int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, float scale, void* stream) {
+    return launch_dwtsvd_embed(src, dst, plane, wm_packed, n_wm_rows, wm_words, wm_len, frame_wm_row, scale, (cudaStream_t)stream);
 }
 
 B200WM_API int b200wm_dwtsvd_embed_copies(const void* src, const b200wm_plane* plane, void* dst, int64_t copy_stride_bytes,
@@ -136,9 +136,9 @@ B200WM_API int b200wm_dct8_masks(const void* lum, const b200wm_plane* lum_plane,
 }
 
 B200WM_API int b200wm_dct8_embed(const void* src, void* dst, const b200wm_plane* plane, const float* block_mean,
-                      const float* tex_mask, const double* frame_sum, const uint32_t* wm_packed, int32_t wm_words,
-                      int64_t wm_len, const int32_t* frame_wm_row, float alpha, void* stream) {
-    return launch_dct8_embed(src, dst, plane, block_mean, tex_mask, frame_sum, wm_packed, wm_words, wm_len, frame_wm_row,
+                      const float* tex_mask, const double* frame_sum, const uint32_t* wm_packed, int32_t n_wm_rows,
+                      int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, float alpha, void* stream) {
+    return launch_dct8_embed(src, dst, plane, block_mean, tex_mask, frame_sum, wm_packed, n_wm_rows, wm_words, wm_len, frame_wm_row,
                              alpha, (cudaStream_t)stream);
 }
 
@@ -191,8 +191,8 @@ B200WM_API int b200wm_attack_resize(const void* src, const b200wm_plane* src_pla
 
 B200WM_API int b200wm_dwtsvd_embed_rgb8(const uint8_t* src, uint8_t* dst, int32_t n_frames, int32_t height, int32_t width,
                             int64_t pitch_bytes, int64_t frame_stride_bytes, const float* scales, const uint32_t* wm_packed,
-                            int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, void* stream) {
-    return launch_embed_rgb8(src, dst, n_frames, height, width, pitch_bytes, frame_stride_bytes, scales, wm_packed, wm_words,
+                            int32_t n_wm_rows, int32_t wm_words, int64_t wm_len, const int32_t* frame_wm_row, void* stream) {
+    return launch_embed_rgb8(src, dst, n_frames, height, width, pitch_bytes, frame_stride_bytes, scales, wm_packed, n_wm_rows, wm_words,
                              wm_len, frame_wm_row, (cudaStream_t)stream);
 }
 

@@ -207,7 +207,7 @@ __device__ __forceinline__ float project21(const float (&b)[64], const float (&b
 struct DctWm {
     const uint32_t* wm;
     const int32_t* frame_row;
-    int wm_words;
+    int n_rows, wm_words;
     double alpha;
 };
 
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kDctThreads, kVec ? B200WM_DCT_EMBED_MIN_CTAS 
     const long long o = (long long)frame * g.nb + c;
     const double mask = (double)tex_mask[o] * luminance_mask((double)block_mean[o], frame_sum[frame], g.nb);
     const double step = wm.alpha * mask, step2 = step + step;
-    const int row = wm.frame_row ? wm.frame_row[frame] : 0;
+    const int row = wm.frame_row ? min(max(wm.frame_row[frame], 0), wm.n_rows - 1) : 0;
     const int bit = (wm.wm[(long long)row * wm.wm_words + (c >> 5)] >> (c & 31)) & 1;
     // coeffs[2][1] = sign(c) * (floor(|c| / step2) * step2 [+ step]); np.sign(0) == 0 (dct_encoder.py:33,35)
     double base = floor(fabs((double)c21) / step2) * step2;
@@ -367,17 +367,17 @@ int launch_dct8_masks(const void* lum, const b200wm_plane* pl, float* block_mean
 }
 
 int launch_dct8_embed(const void* src, void* dst, const b200wm_plane* pl, const float* block_mean, const float* tex_mask,
-                      const double* frame_sum, const uint32_t* wm, int wm_words, long long wm_len,
+                      const double* frame_sum, const uint32_t* wm, int n_wm_rows, int wm_words, long long wm_len,
                       const int32_t* frame_row, float alpha, cudaStream_t stream) {
     int rc = validate_plane(pl);
     if (rc) return rc;
-    if (!src || !dst || !block_mean || !tex_mask || !frame_sum || !wm || wm_words <= 0 || !(alpha > 0.0f))
+    if (!src || !dst || !block_mean || !tex_mask || !frame_sum || !wm || n_wm_rows <= 0 || wm_words <= 0 || !(alpha > 0.0f))
         return B200WM_ERR_INVALID;
     const BlockGeom g = make_block_geom(pl->height, pl->width);
     if (wm_len < g.nb || (long long)wm_words * 32 < g.nb) return B200WM_ERR_SHORT_WM;
     if (g.nb == 0 || pl->n_frames == 0) return B200WM_OK;
     const DctPlane dp = make_dct_plane(src, dst, pl);
-    const DctWm w{wm, frame_row, wm_words, (double)alpha};
+    const DctWm w{wm, frame_row, n_wm_rows, wm_words, (double)alpha};
     const unsigned gx = (g.nb + kDctThreads - 1) / kDctThreads;
     FOR_FRAME_CHUNKS(pl->n_frames, gx, {
         if (dp.is_f32) dct8_embed_kernel<float, false><<<grid, kDctThreads, 0, stream>>>(dp, g, block_mean, tex_mask, frame_sum, w, f0);

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kThreads, kMode == 0 ? 8 : 1) dwtsvd_embed_ker
     if (c >= (unsigned)g.n_tiles) return;
     const unsigned ty = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
     const unsigned tx = c - ty * g.tiles_x;
-    const int row = em.frame_row ? em.frame_row[frame] : 0;
+    const int row = em.frame_row ? clamp_row(em.frame_row[frame], em.n_rows) : 0;
     const int bit = (em.wm[(long long)row * em.wm_words + (c >> 5)] >> (c & 31)) & 1;
 
     const long long off = frame * pl.frame_stride + (unsigned long long)(ty * 8) * pl.pitch;
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_sigma_dct_kernel(PlaneArgs pl
 #pragma unroll
     for (int j = 0; j < 4; ++j) dct4_1d(B[j], B[4 + j], B[8 + j], B[12 + j]);
     float v[4];
-    bool zero;
-    sigma[(long long)frame * g.n_tiles + c] = top_singular<false>(B, v, zero);
+    bool zero, maybe_flat;
+    sigma[(long long)frame * g.n_tiles + c] = top_singular<false>(B, v, zero, maybe_flat);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -268,17 +268,17 @@ int validate_plane(const b200wm_plane* pl) {
     return B200WM_OK;
 }
 
-int launch_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* pl, const uint32_t* wm, int wm_words,
+int launch_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* pl, const uint32_t* wm, int n_wm_rows, int wm_words,
                         long long wm_len, const int32_t* frame_row, float scale, cudaStream_t stream) {
     int rc = validate_plane(pl);
     if (rc) return rc;
-    if (!src || !dst || !wm || wm_words <= 0 || !(scale > 0.0f)) return B200WM_ERR_INVALID;
+    if (!src || !dst || !wm || n_wm_rows <= 0 || wm_words <= 0 || !(scale > 0.0f)) return B200WM_ERR_INVALID;
     const TileGeom g = make_geom(pl->height, pl->width);
     if (wm_len < g.n_tiles || (long long)wm_words * 32 < g.n_tiles) return B200WM_ERR_SHORT_WM;
     if (g.n_tiles == 0 || pl->n_frames == 0) return B200WM_OK;
     if ((uintptr_t)src % 4 && pl->dtype == B200WM_F32) return B200WM_ERR_INVALID;
     PlaneArgs pa{(const uint8_t*)src, (uint8_t*)dst, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
-    EmbedArgs ea{wm, frame_row, wm_words, scale, 1.0f / scale};
+    EmbedArgs ea{wm, frame_row, n_wm_rows, wm_words, scale, 1.0f / scale};
     if (g_path == 0 && tma_eligible(src, dst, pl, g)) return launch_dwtsvd_embed_tma(src, dst, pl, g, ea, stream);
     const int mode = plane_mode(src, dst, pl);
     const unsigned gx = (g.n_tiles + kThreads - 1) / kThreads;
@@ -327,7 +327,12 @@ int launch_dwtsvd_extract(const void* src, const b200wm_plane* pl, float scale, 
     const bool fused = pos_counts && payload_len <= 32 && (32 % payload_len) == 0;
     if (pos_counts && fused)
         B200WM_CUDA_TRY(cudaMemsetAsync(pos_counts, 0, sizeof(int32_t) * (size_t)pl->n_frames * payload_len, stream));
-    if (g.words > 0) {
+    if (g.words > 0 && g.n_tiles == 0) {
+        // a plane with a dimension below 8 (e.g. 4 x 64) has raw-bit words but no tile: nothing to read
+        B200WM_CUDA_TRY(cudaMemsetAsync(raw_bits, 0, sizeof(uint32_t) * (size_t)pl->n_frames * g.words, stream));
+        if (pos_counts && !fused)
+            B200WM_CUDA_TRY(cudaMemsetAsync(pos_counts, 0, sizeof(int32_t) * (size_t)pl->n_frames * payload_len, stream));
+    } else if (g.words > 0) {
         PlaneArgs pa{(const uint8_t*)src, nullptr, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
         ExtractArgs xa{raw_bits, fused ? pos_counts : nullptr, sigma, payload_len, fused ? every_mask(payload_len) : 0u, scale, 1.0f / scale};
         if (g_path == 0 && !sigma && tma_eligible(src, src, pl, g)) {

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_copies_kernel(PlaneArgs
         }
 #pragma unroll 1
         for (int k = 0; k < cp.n_copies; ++k) {
-            const int row = rows_of_frame ? rows_of_frame[k] : k;
+            const int row = clamp_row(rows_of_frame ? rows_of_frame[k] : k, em.n_rows);
             const int bit = (wm_word[(long long)row * em.wm_words] >> (c & 31)) & 1;
             embed_copy_deltas(bp, bit, em.scale, 12582912.0f, D);
             uint8_t* o = cp.dst + k * cp.copy_stride + o0;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_embed_copies_kernel(PlaneArgs
         }
 #pragma unroll 1
         for (int k = 0; k < cp.n_copies; ++k) {
-            const int row = rows_of_frame ? rows_of_frame[k] : k;
+            const int row = clamp_row(rows_of_frame ? rows_of_frame[k] : k, em.n_rows);
             const int bit = (wm_word[(long long)row * em.wm_words] >> (c & 31)) & 1;
             embed_copy_deltas(bp, bit, em.scale, 0.0f, D);
             uint8_t* o = cp.dst + k * cp.copy_stride + off + (long long)tx * 8 * es;
@@ -99,7 +99,7 @@ int launch_dwtsvd_embed_copies(const void* src, const b200wm_plane* pl, void* ds
                          (copy_stride % 8) == 0 && ((uintptr_t)src % 8) == 0 && ((uintptr_t)dst % 8) == 0;
     PlaneArgs pa{(const uint8_t*)src, nullptr, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
     CopyArgs ca{(uint8_t*)dst, copy_stride, copy_row, n_copies};
-    EmbedArgs ea{wm, nullptr, wm_words, scale, 1.0f / scale};
+    EmbedArgs ea{wm, nullptr, n_wm_rows, wm_words, scale, 1.0f / scale};
     const unsigned gx = (g.n_tiles + kThreads - 1) / kThreads;
     for (int f0 = 0; f0 < pl->n_frames; f0 += 65535) {
         const dim3 grid(gx, (unsigned)((pl->n_frames - f0) < 65535 ? (pl->n_frames - f0) : 65535));

@@ -26,6 +26,7 @@ __device__ __forceinline__ uint8_t* row_ptr(uint8_t* p, unsigned r, unsigned pit
 struct EmbedArgs {
     const uint32_t* wm;       // [rows, wm_words]
     const int32_t* frame_row; // nullable
+    int n_rows;               // rows of wm; row indices are clamped into [0, n_rows) (never an out-of-bounds read)
     int wm_words;
     float scale, inv_scale;
 };
@@ -38,6 +39,8 @@ struct ExtractArgs {
     unsigned every;           // bit i*payload_len set for every i (payload_len divides 32), else 0
     float scale, inv_scale;
 };
+
+__device__ __forceinline__ int clamp_row(int row, int n_rows) { return min(max(row, 0), n_rows - 1); }
 
 inline unsigned every_mask(int payload_len) {
     if (payload_len <= 0 || payload_len > 32 || 32 % payload_len) return 0u;
@@ -55,8 +58,9 @@ inline unsigned every_mask(int payload_len) {
 // are exact on a constant block, so sigma_0 = 16*fl(c*fl(c*|v|)) (checked against the oracle for every
 // uint8 v and random float v in tests/test_oracle_golden.py).  E.g. a flat 255 tile has sigma_0 =
 // 2039.99988 (bit 1, floor 135), not 2040 (bit 0, floor 136); black 0/16 and white 235 are no boundary cases.
-// So: when sigma_0 lands within 2^-21 (relative) of a boundary - rare - the kernel probes whether the tile
-// is flat and, if so, takes the reference's value.  Non-flat tiles on a boundary stay what they are:
+// So: when the eigen-iteration reports a possibly flat block (one compare, svd4.cuh) whose sigma_0 lands
+// within 2^-21 (relative) of a boundary, the kernel probes whether the tile is flat and, if so, takes the
+// reference's value.  Non-flat tiles on a boundary stay what they are:
 // decided by float32 rounding inside cv2.dct / sgesdd, which no independent implementation reproduces.
 constexpr float kHaarTap = 0.70710677f;          // float32(1/sqrt(2))
 __device__ __forceinline__ float flat_sigma_ref(float sample) {
@@ -178,17 +182,17 @@ template <bool kStash, typename Probe>
 __device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scale, float inv_scale,
                                              float bias, float (&D)[16], float4* stash, Probe probe) {
     float v[4];
-    bool zero;
+    bool zero, maybe_flat;
     if (kStash) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)   // asm: the compiler must not forward these stores to the loads below
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)),
                          "f"(S[4 * i]), "f"(S[4 * i + 1]), "f"(S[4 * i + 2]), "f"(S[4 * i + 3]) : "memory");
     }
-    float sigma = 0.5f * top_singular<true>(S, v, zero);   // sigma_0 of the LL block
+    float sigma = 0.5f * top_singular<true>(S, v, zero, maybe_flat);   // sigma_0 of the LL block
     float q, rem;
     floor_divmod(sigma, scale, inv_scale, q, rem);
-    if (on_boundary<false>(sigma, rem, scale)) {
+    if (maybe_flat && on_boundary<false>(sigma, rem, scale)) {
         const float flat = probe();
         if (flat == flat) {
             sigma = flat_sigma_ref(flat);
@@ -230,10 +234,11 @@ struct BlockPair {
 
 template <typename Probe>
 __device__ __forceinline__ void embed_prepare(const float (&S)[16], float scale, float inv_scale, BlockPair& bp, Probe probe) {
-    bp.sigma = 0.5f * top_singular<true>(S, bp.v, bp.zero);
+    bool maybe_flat;
+    bp.sigma = 0.5f * top_singular<true>(S, bp.v, bp.zero, maybe_flat);
     float rem;
     floor_divmod(bp.sigma, scale, inv_scale, bp.q, rem);
-    if (on_boundary<false>(bp.sigma, rem, scale)) {
+    if (maybe_flat && on_boundary<false>(bp.sigma, rem, scale)) {
         const float flat = probe();
         if (flat == flat) {
             bp.sigma = flat_sigma_ref(flat);
@@ -264,11 +269,11 @@ __device__ __forceinline__ void embed_copy_deltas(const BlockPair& bp, int bit, 
 template <typename Probe>
 __device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, float inv_scale, float& sigma, Probe probe) {
     float v[4];
-    bool zero;
-    sigma = 0.5f * top_singular<false>(S, v, zero);
+    bool zero, maybe_flat;
+    sigma = 0.5f * top_singular<false>(S, v, zero, maybe_flat);
     float q, rem;
     floor_divmod(sigma, scale, inv_scale, q, rem);
-    if (on_boundary<true>(sigma, rem, scale)) {
+    if (maybe_flat && on_boundary<true>(sigma, rem, scale)) {
         const float flat = probe();
         if (flat == flat) {
             sigma = flat_sigma_ref(flat);
@@ -320,8 +325,8 @@ __device__ __forceinline__ unsigned extract_bits_x2(const f2 (&S)[16], float sca
     f2 sigma = mul2(bc2(0.5f), p.sigma0);
     f2 q, rem;
     floor_divmod2(sigma, scale, inv_scale, q, rem);
-    const bool edge_x = on_boundary<true>(sigma.x, rem.x, scale), edge_y = on_boundary<true>(sigma.y, rem.y, scale);
-    if (edge_x | edge_y) {
+    if (p.flat_x | p.flat_y) {
+        const bool edge_x = p.flat_x && on_boundary<true>(sigma.x, rem.x, scale), edge_y = p.flat_y && on_boundary<true>(sigma.y, rem.y, scale);
         const float fx = edge_x ? probe(0) : __int_as_float(0x7FC00000), fy = edge_y ? probe(1) : __int_as_float(0x7FC00000);
         if (fx == fx) sigma.x = flat_sigma_ref(fx);
         if (fy == fy) sigma.y = flat_sigma_ref(fy);
@@ -340,8 +345,8 @@ __device__ __forceinline__ void embed_deltas_x2(const f2 (&S)[16], unsigned bits
     f2 sigma = mul2(bc2(0.5f), p.sigma0);
     f2 q, rem;
     floor_divmod2(sigma, scale, inv_scale, q, rem);
-    const bool edge_x = on_boundary<false>(sigma.x, rem.x, scale), edge_y = on_boundary<false>(sigma.y, rem.y, scale);
-    if (edge_x | edge_y) {
+    if (p.flat_x | p.flat_y) {
+        const bool edge_x = p.flat_x && on_boundary<false>(sigma.x, rem.x, scale), edge_y = p.flat_y && on_boundary<false>(sigma.y, rem.y, scale);
         const float fx = edge_x ? probe(0) : __int_as_float(0x7FC00000), fy = edge_y ? probe(1) : __int_as_float(0x7FC00000);
         if (fx == fx) sigma.x = flat_sigma_ref(fx);
         if (fy == fy) sigma.y = flat_sigma_ref(fy);

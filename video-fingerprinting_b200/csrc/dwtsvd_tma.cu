@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
         const TilePair<kNarrow> tp(t, it, sg, sp);
         // the watermark bits of this warp's tiles (32 per half), funnel-shifted out of the packed row;
         // issued before the wait so that their latency hides behind it
-        const int row = em.frame_row ? em.frame_row[it.frame] : 0;
+        const int row = em.frame_row ? clamp_row(em.frame_row[it.frame], em.n_rows) : 0;
         const uint32_t* wrow = em.wm + (long long)row * em.wm_words;
         const unsigned c0 = (unsigned)(it.ty * g.tiles_x + it.cx * sg.chunk_tiles + (t & ~31));
         unsigned wbits[2];

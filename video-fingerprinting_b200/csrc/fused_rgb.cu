@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128, 4) dwtsvd_embed_rgb8_kernel(RgbArgs a, Em
     if (c >= (unsigned)g.n_tiles) return;
     const unsigned ty = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
     const unsigned tx = c - ty * g.tiles_x;
-    const int row = em.frame_row ? em.frame_row[frame] : 0;
+    const int row = em.frame_row ? clamp_row(em.frame_row[frame], em.n_rows) : 0;
     const int bit = (em.wm[(long long)row * em.wm_words + (c >> 5)] >> (c & 31)) & 1;
     const long long off = frame * a.frame_stride + (unsigned long long)(ty * 8) * a.pitch + tx * 24;
 
@@ -207,18 +207,18 @@ static int check_rgb(const void* src, int n_frames, int height, int width, long 
 }
 
 int launch_embed_rgb8(const uint8_t* src, uint8_t* dst, int n_frames, int height, int width, long long pitch,
-                      long long frame_stride, const float* scales, const uint32_t* wm, int wm_words, long long wm_len,
+                      long long frame_stride, const float* scales, const uint32_t* wm, int n_wm_rows, int wm_words, long long wm_len,
                       const int32_t* frame_row, cudaStream_t stream) {
     int rc = check_rgb(src, n_frames, height, width, pitch, frame_stride);
     if (rc) return rc;
-    if (!dst || !scales || !wm || wm_words <= 0) return B200WM_ERR_INVALID;
+    if (!dst || !scales || !wm || n_wm_rows <= 0 || wm_words <= 0) return B200WM_ERR_INVALID;
     const TileGeom g = make_geom(height, width);
     const int mask = (scales[0] > 0.0f ? 1 : 0) | (scales[1] > 0.0f ? 2 : 0) | (scales[2] > 0.0f ? 4 : 0);
     if (mask == 0) return B200WM_OK;             // nothing to mark: the reference's loop skips every channel
     if (wm_len < g.n_tiles || (long long)wm_words * 32 < g.n_tiles) return B200WM_ERR_SHORT_WM;
     if (g.n_tiles == 0 || n_frames == 0) return B200WM_OK;
     RgbArgs a{src, dst, frame_stride, (unsigned)pitch, {scales[0], scales[1], scales[2]}};
-    EmbedArgs ea{wm, frame_row, wm_words, 0.0f, 0.0f};
+    EmbedArgs ea{wm, frame_row, n_wm_rows, wm_words, 0.0f, 0.0f};
     const bool aligned = ((uintptr_t)src % 8) == 0 && ((uintptr_t)dst % 8) == 0 && pitch % 8 == 0 && frame_stride % 8 == 0;
     const unsigned gx = (g.n_tiles + 127) / 128;
     for (int f0 = 0; f0 < n_frames; f0 += 65535) {

@@ -11,7 +11,7 @@
 namespace b200wm {
 
 int validate_plane(const b200wm_plane* pl);
-int launch_dwtsvd_embed(const void*, void*, const b200wm_plane*, const uint32_t*, int, long long, const int32_t*, float,
+int launch_dwtsvd_embed(const void*, void*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float,
                         cudaStream_t);
 int launch_dwtsvd_extract(const void*, const b200wm_plane*, float, uint32_t*, int, int, int32_t*, float*, cudaStream_t);
 int launch_vote_finish(const int32_t*, int, int, long long, const int32_t*, uint8_t*, uint64_t*, cudaStream_t);
@@ -192,7 +192,7 @@ int mark_host(const uint8_t* src, uint8_t* dst, const b200wm_plane* pl, const ui
         if ((rc = copy_planes(buf, src + (size_t)f0 * pl->frame_stride_bytes, &host, m, true, c->up))) return rc;
         B200WM_CUDA_TRY(cudaEventRecord(c->uploaded[s], c->up));
         B200WM_CUDA_TRY(cudaStreamWaitEvent(c->run, c->uploaded[s], 0));
-        if ((rc = launch_dwtsvd_embed(buf, buf, &devp, (const uint32_t*)c->wm.p, wm_words, wm_len,
+        if ((rc = launch_dwtsvd_embed(buf, buf, &devp, (const uint32_t*)c->wm.p, n_rows, wm_words, wm_len,
                                       frame_row_host ? (const int32_t*)c->rows.p + f0 : nullptr, scale, c->run)))
             return rc;
         B200WM_CUDA_TRY(cudaEventRecord(c->computed[s], c->run));
@@ -326,7 +326,7 @@ int mark_verify_host(const uint8_t* src, uint8_t* dst, const b200wm_plane* pl, c
         if ((rc = copy_planes(buf, src + (size_t)f0 * pl->frame_stride_bytes, &host, m, true, c->up))) return rc;
         B200WM_CUDA_TRY(cudaEventRecord(c->uploaded[s], c->up));
         B200WM_CUDA_TRY(cudaStreamWaitEvent(c->run, c->uploaded[s], 0));
-        if ((rc = launch_dwtsvd_embed(buf, buf, &devp, (const uint32_t*)c->wm.p, wm_words, wm_len,
+        if ((rc = launch_dwtsvd_embed(buf, buf, &devp, (const uint32_t*)c->wm.p, n_rows, wm_words, wm_len,
                                       frame_row_host ? (const int32_t*)c->rows.p + f0 : nullptr, scale, c->run)))
             return rc;
         if ((rc = launch_dwtsvd_extract(buf, &devp, scale, raw, g.words, payload_len, cnt, nullptr, c->run))) return rc;

@@ -163,8 +163,12 @@ __device__ __forceinline__ bool rayleigh_check(const float (&x)[4], const float 
 }
 
 // sigma0 = largest singular value of S (not squared); v = unit right singular vector.
+// maybe_flat: the first two components of the second power iterate are bitwise equal - necessary for a block
+// with sixteen equal entries (every entry of G, hence of G*1 and G*G*1, is then the same number) and next to
+// never true otherwise; callers use it as the one-instruction filter in front of the flat-tile rule of
+// dwtsvd_tile.cuh.
 template <bool kWantVec>
-__device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4], bool& zero_block) {
+__device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4], bool& zero_block, bool& maybe_flat) {
     float G[10];
     gram4(S, G);
     const float tr_raw = (G[0] + G[4]) + (G[7] + G[9]);
@@ -184,6 +188,7 @@ __device__ __forceinline__ float top_singular(const float (&S)[16], float (&v)[4
     w[2] = (G[2] + G[5]) + (G[7] + G[8]);
     w[3] = (G[3] + G[6]) + (G[8] + G[9]);
     symv4(G, w, x);                              // second power step, unchecked: one step alone almost never certifies
+    maybe_flat = x[0] == x[1];
     symv4(G, x, w);
     float xw, xx;
     bool done = rayleigh_check(x, w, tr, xw, xx) || zero_block;

@@ -83,6 +83,7 @@ __device__ __forceinline__ void floor_divmod2(f2 x, float m, float inv_m, f2& q,
 struct Pair2 {          // per-lane outputs of the packed routine
     f2 sigma0;          // largest singular value of S (not halved)
     bool zero_x, zero_y;
+    bool flat_x, flat_y;   // maybe_flat of svd4.cuh, per lane
 };
 
 static __device__ __noinline__ Top5 top_singular_scalar(float s0, float s1, float s2, float s3, float s4, float s5, float s6, float s7,
@@ -90,9 +91,9 @@ static __device__ __noinline__ Top5 top_singular_scalar(float s0, float s1, floa
                                                  float s15) {
     const float S[16] = {s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15};
     float v[4];
-    bool zero;
+    bool zero, flat;
     Top5 t;
-    t.sigma = top_singular<true>(S, v, zero);
+    t.sigma = top_singular<true>(S, v, zero, flat);
     t.v0 = v[0]; t.v1 = v[1]; t.v2 = v[2]; t.v3 = v[3];
     return t;
 }
@@ -118,6 +119,8 @@ __device__ __forceinline__ Pair2 top_singular_x2(const f2 (&S)[16], f2 (&v)[4]) 
     w[2] = add2(add2(G[2], G[5]), add2(G[7], G[8]));
     w[3] = add2(add2(G[3], G[6]), add2(G[8], G[9]));
     symv4x2(G, w, x);
+    out.flat_x = x[0].x == x[1].x;
+    out.flat_y = x[0].y == x[1].y;
     symv4x2(G, x, w);
     // rayleigh_check, two lanes
     const f2 xw = dot4x2(x, w), xx = dot4x2(x, x);

@@ -37,17 +37,35 @@ class FrameOnDevice:
         return self.src
 
 
-class RawBits(np.ndarray):
-    """float64 (1, N) array of raw bits, as the reference's ``decode`` returns, that also keeps
-    the packed bits and per-position counts the extract kernel left on the GPU so that
-    ``DeShuffler.degenerate`` can finish the vote there."""
+class Staging:
+    """Pinned host buffers for the batched drivers: frames are gathered into ``up`` (one H2D copy per batch at
+    full link speed instead of one pageable copy per frame) and results land in ``down``.  Grown on demand,
+    reused between batches."""
 
-    def __new__(cls, values, packed=None, block_num=None):
-        obj = np.asarray(values, dtype=np.float64).view(cls)
-        obj.packed = packed
-        obj.block_num = block_num
-        return obj
+    def __init__(self):
+        self.up = self.down = None
 
-    def __array_finalize__(self, obj):
-        self.packed = getattr(obj, "packed", None)
-        self.block_num = getattr(obj, "block_num", None)
+    def _fit(self, buf, shape):
+        n = int(np.prod(shape))
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        return buf
+
+    def upload(self, frames, device):
+        """list of equal-shape uint8 arrays -> CUDA tensor [N, *shape] (async on the current stream)."""
+        shape = (len(frames),) + tuple(frames[0].shape)
+        self.up = self._fit(self.up, shape)
+        host = self.up[:int(np.prod(shape))].view(shape)
+        view = host.numpy()
+        for i, f in enumerate(frames):
+            np.copyto(view[i], f, casting="unsafe")
+        return host.to(device, non_blocking=True)
+
+    def download(self, tensor):
+        """CUDA uint8 tensor -> numpy view of the pinned ``down`` buffer (valid until the next download)."""
+        shape = tuple(tensor.shape)
+        self.down = self._fit(self.down, shape)
+        host = self.down[:tensor.numel()].view(shape)
+        host.copy_(tensor, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()

@@ -12,6 +12,8 @@ class DeGrayScale(DeShuffler):
         self.payload_shape = payload_shape
         return super().set_shape(payload_shape)
 
+    def format_pattern(self, pattern):
+        return (np.asarray(pattern).astype(np.uint8) * 255).reshape(self.payload_shape)
+
     def degenerate(self, wm_bits):
-        res = self._patterns(wm_bits)[0].cpu().numpy().astype(np.uint8) * 255
-        return res.reshape(self.payload_shape)
+        return self.format_pattern(self._patterns(wm_bits)[0].cpu().numpy())

@@ -2,7 +2,7 @@
 import numpy as np
 
 from b200wm import ops
-from .._frames import FrameOnDevice, RawBits
+from .._frames import FrameOnDevice
 
 
 class DctDecoder:
@@ -19,5 +19,4 @@ class DctDecoder:
         block_num = rows * cols // 8 // 8
         masks = ops.dct8_masks(frame.dev, channel=0)
         raw, _ = ops.dct8_extract(frame.dev, masks, alpha=self.alpha, channel=1)
-        bits = ops.unpack_bits(raw, block_num).astype(np.float64).reshape(1, -1)
-        return RawBits(bits, packed=raw, block_num=block_num)
+        return ops.unpack_bits(raw, block_num).astype(np.float64).reshape(1, -1)

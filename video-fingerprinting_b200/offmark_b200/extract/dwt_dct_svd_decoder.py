@@ -2,7 +2,7 @@
 import numpy as np
 
 from b200wm import ops
-from .._frames import FrameOnDevice, RawBits
+from .._frames import FrameOnDevice
 
 
 class DwtDctSvdDecoder:
@@ -28,8 +28,7 @@ class DwtDctSvdDecoder:
         if self.scales[1] <= 0:
             return np.zeros((1, self.block_num))
         raw, _ = ops.dwtsvd_extract(frame.dev, scale=self.scales[1], channel=1)
-        bits = ops.unpack_bits(raw, self.block_num).astype(np.float64).reshape(1, -1)
-        return RawBits(bits, packed=raw, block_num=self.block_num)
+        return ops.unpack_bits(raw, self.block_num).astype(np.float64).reshape(1, -1)
 
     def decode_rgb8(self, frame):
         """uint8 ``[H, W, 3]`` CUDA frame -> the same ``(1, N)`` float64 array as ``decode`` of its YUV
@@ -39,8 +38,7 @@ class DwtDctSvdDecoder:
         if self.scales[1] <= 0:
             return np.zeros((1, self.block_num))
         raw, _ = ops.dwtsvd_extract_rgb8(frame, scale=self.scales[1], channel=1)
-        bits = ops.unpack_bits(raw, self.block_num).astype(np.float64).reshape(1, -1)
-        return RawBits(bits, packed=raw, block_num=self.block_num)
+        return ops.unpack_bits(raw, self.block_num).astype(np.float64).reshape(1, -1)
 
     def decode_planes(self, planes, scale=None, payload_len=None):
         """Batched form for device-resident planes: -> (raw_bits int32 [N, words],

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from b200wm import ops
-from .._frames import device_of
+from .._frames import device_of, Staging
 
 logger = logging.getLogger(__name__)
 
@@ -21,6 +21,7 @@ class Embedder:
         self.frame_embedder = frame_embedder
         self.device = device
         self.batch_frames = max(1, int(batch_frames))      # optional extension: frames per kernel launch
+        self._staging = Staging()
 
     def start(self):
         logger.debug('Entering start()')
@@ -50,8 +51,10 @@ class Embedder:
         same = all(f.shape == pending[0].shape for f in pending)
         groups = [pending] if same else [[f] for f in pending]
         for group in groups:
-            frames = torch.from_numpy(np.stack(group)).to(dev)
-            marked = self.frame_embedder.mark_rgb8(frames).cpu().numpy()
+            frames = self._staging.upload(group, dev)
+            # views of a pinned buffer that the next batch overwrites: writers consume a frame inside write(), as
+            # the reference's FileEncoder does (video/frame_writer.py:41-44 serialises it straight into the pipe)
+            marked = self._staging.download(self.frame_embedder.mark_rgb8(frames))
             for f in marked:
                 self.frame_writer.write(f)
         pending.clear()

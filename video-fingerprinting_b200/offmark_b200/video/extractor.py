@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from b200wm import ops
-from .._frames import device_of
+from .._frames import device_of, Staging
 
 logger = logging.getLogger(__name__)
 
@@ -21,6 +21,7 @@ class Extractor:
         self.device = device
         self.batch_frames = max(1, int(batch_frames))      # optional extension: frames per kernel launch
         self.patterns = []                                 # optional extension: every pattern that was logged
+        self._staging = Staging()
 
     def start(self):
         logger.debug('Entering start()')
@@ -53,7 +54,7 @@ class Extractor:
         dev = device_of(self.device)
         same = all(f.shape == pending[0].shape for f in pending)
         for group in ([pending] if same else [[f] for f in pending]):
-            frames = torch.from_numpy(np.stack(group)).to(dev)
+            frames = self._staging.upload(group, dev)
             h, w = frames.shape[1], frames.shape[2]
             scale = self.frame_extractor.scales[1]
             length = self.degenerator.payload_len
@@ -63,8 +64,9 @@ class Extractor:
                 continue
             raw, counts = ops.dwtsvd_extract_rgb8(frames, scale=scale, channel=1, payload_len=length)
             patterns, _ = self.degenerator.degenerate_counts(counts, h * w // 64)
+            fmt = getattr(self.degenerator, "format_pattern", None)
             for p in patterns.cpu().numpy():
-                self._log(p)
+                self._log(fmt(p) if fmt else p)
         pending.clear()
 
     def check_frame(self, frame_rgb):

@@ -5,6 +5,9 @@ frame_writer.py); decode/encode stay outside this repository's scope, so the dri
 from arrays with the same ``width`` / ``height`` / ``read()`` / ``write()`` / ``close()`` surface."""
 
 
+import numpy as np
+
+
 class ArrayReader:
     def __init__(self, frames):
         self._frames = iter(frames)
@@ -23,7 +26,7 @@ class ArrayWriter:
         self.frames = []
 
     def write(self, frame):
-        self.frames.append(frame)
+        self.frames.append(np.array(frame))      # a copy: the frame is consumed inside write(), like a pipe would
 
     def close(self):
         pass
