@@ -225,6 +225,13 @@ B200WM_API int b200wm_pattern_hist(const uint64_t* packed, const int32_t* frame_
                         int32_t* hist, int32_t* first_seen, int32_t* bit_votes,
                         int32_t* seg_frames, void* stream);
 
+/*
+ * Reset of a vote state that lives in ONE int32 run [counters (hist | bit_votes | seg_frames) | first_seen]: the
+ * first n_zero entries become 0, the rest INT32_MAX ("no patterns collected",
+ * tests/segment_mark_detect_hls.py:140-142), in one launch - so that a state can be kept and reused per batch.
+ */
+B200WM_API int b200wm_vote_state_reset(int32_t* state, int64_t n_zero, int64_t n_total, void* stream);
+
 /* ---- colour bracket (video/embedder.py:33-39, video/extractor.py:30-34) ------------- */
 /*
  * uint8 H x W x 3 interleaved frames (what FileDecoder.read returns,

@@ -104,7 +104,14 @@ def _vote_worker(rank, world, port, L, all_patterns, out_q):
     vote = SegmentVote(1, L, "cpu")
     _fill_vote_state(vote, mine, [0] * len(mine), range(a, b))
     vote.combine()
+    first_round = vote.result()[0]
+    # the same state object serves the next batch: reset, refill, asynchronous combine joined by result()
+    vote.reset()
+    assert vote.result()[0][0] is None
+    _fill_vote_state(vote, mine, [0] * len(mine), range(a, b))
+    vote.combine(async_op=True)
     pattern, freq, bit_votes, frames = vote.result()[0]
+    assert pattern.tolist() == first_round[0].tolist() and freq == first_round[1] and frames == first_round[3]
     bits = torch.tensor([[(p >> (L - 1 - j)) & 1 for j in range(L)] for p in mine], dtype=torch.uint8).reshape(-1, L)
     gp, gf = gathered_pattern_vote(bits, torch.arange(a, b))
     out_q.put((rank, pattern.tolist(), freq, bit_votes.tolist(), frames, gp.tolist(), gf))
@@ -142,17 +149,25 @@ def _owned_vote_worker(rank, world, port, L, per_segment, out_q):
     n_seg = len(per_segment)
     per = n_seg // world
     vote = SegmentVote(n_seg, L, "cpu", owned=(rank * per, per))
-    state, first = vote._mine()
-    order = 0
-    for s in range(rank * per, (rank + 1) * per):           # whole segments live on one rank (config 4)
-        for p in per_segment[s]:
-            state["hist"][s - first, p] += 1
-            state["first_seen"][s - first, p] = min(int(state["first_seen"][s - first, p]), order)
-            state["seg_frames"][s - first] += 1
-            for j in range(L):
-                state["bit_votes"][s - first, j] += (p >> (L - 1 - j)) & 1
-            order += 1
+
+    def fill():
+        state, first = vote._mine()
+        order = 0
+        for s in range(rank * per, (rank + 1) * per):           # whole segments live on one rank (config 4)
+            for p in per_segment[s]:
+                state["hist"][s - first, p] += 1
+                state["first_seen"][s - first, p] = min(int(state["first_seen"][s - first, p]), order)
+                state["seg_frames"][s - first] += 1
+                for j in range(L):
+                    state["bit_votes"][s - first, j] += (p >> (L - 1 - j)) & 1
+                order += 1
+    fill()
     vote.combine()
+    once = [(None if r[0] is None else r[0].tolist(), r[1], r[2].tolist(), r[3]) for r in vote.result()]
+    vote.reset()                                                # persistent state: next batch, overlapped combine
+    fill()
+    vote.combine(async_op=True)
+    assert once == [(None if r[0] is None else r[0].tolist(), r[1], r[2].tolist(), r[3]) for r in vote.result()]
     out_q.put((rank, [(None if r[0] is None else r[0].tolist(), r[1], r[2].tolist(), r[3]) for r in vote.result()]))
     dist.destroy_process_group()
 

@@ -319,6 +319,15 @@ def pattern_hist(packed, payload_len, n_segments=1, frame_segment=None, frame_or
     return state
 
 
+def vote_state_reset(flat, n_zero):
+    """``flat`` int32 CUDA tensor: entries [0, n_zero) <- 0, the rest <- INT32_MAX, one launch."""
+    require_cuda()
+    if flat.dtype != torch.int32 or not flat.is_cuda or not flat.is_contiguous():
+        raise ValueError("state must be a contiguous CUDA int32 tensor")
+    check(lib.b200wm_vote_state_reset(_ptr(flat), int(n_zero), flat.numel(), _stream()))
+    return flat
+
+
 # ----------------------------------------------------------------------------- colour bracket
 def bgr8_to_yuv32(frames):
     """uint8 [..., 3] contiguous -> float32 same shape (video/embedder.py:34)."""

@@ -54,6 +54,8 @@ class SegmentVote:
         self._block_len = c + per * bins
         self._flat = torch.zeros(blocks * self._block_len, dtype=torch.int32, device=dev)
         self._n_sum = c
+        self._work = None
+        self._gathered = None
         blk = self._flat.view(blocks, self._block_len)
         self.hist = blk[:, :a].view(blocks, per, bins)
         self.bit_votes = blk[:, a:b].view(blocks, per, self.payload_len)
@@ -63,6 +65,27 @@ class SegmentVote:
         if not self.owned:                # one block: the plain [n_segments, ...] views of the general mode
             self.hist, self.bit_votes = self.hist[0], self.bit_votes[0]
             self.seg_frames, self.first_seen = self.seg_frames[0], self.first_seen[0]
+
+    def reset(self):
+        """Back to "nothing seen" so that ONE state object serves batch after batch: a single kernel launch on the
+        GPU (``b200wm_vote_state_reset``), no allocation.  Waits for a pending asynchronous ``combine`` first."""
+        self.wait()
+        if self._flat.is_cuda:
+            if self.owned:          # per block [counters | first_seen]: reset block by block views of the same run
+                blocks = self.n_segments // self.owned[1]
+                if blocks == 1:
+                    ops.vote_state_reset(self._flat, self._n_sum)
+                else:               # only this rank's block is ever accumulated into; the others are overwritten by the gather
+                    k = self.owned[0] // self.owned[1]
+                    ops.vote_state_reset(self._flat[k * self._block_len:(k + 1) * self._block_len], self._n_sum)
+            else:
+                ops.vote_state_reset(self._flat, self._n_sum)
+        else:
+            blocks = self._flat.numel() // self._block_len
+            blk = self._flat.view(blocks, self._block_len)
+            blk[:, :self._n_sum] = 0
+            blk[:, self._n_sum:] = ops.INT32_MAX
+        return self
 
     def _mine(self):
         """State views that ``b200wm_pattern_hist`` accumulates into and the segment offset it subtracts."""
@@ -86,29 +109,50 @@ class SegmentVote:
         ops.pattern_hist(packed, self.payload_len, n_seg, frame_segment, frame_order, order_offset, state=state)
         return self
 
-    def combine(self, group=None):
+    def combine(self, group=None, async_op=False):
         """Merge the ranks' counters (tens of KB per rank, latency-bound over NVLink).  Owned mode: one
         in-place all-gather of this rank's block.  General mode: one all-gather of the flat state, then SUM
-        of the counters and MIN of the first-seen indices locally.  No-op without a process group."""
+        of the counters and MIN of the first-seen indices locally.  No-op without a process group.
+
+        ``async_op=True`` enqueues the collective behind the work already on the current stream and returns
+        at once WITHOUT making the current stream wait for it, so that the next batch's embed overlaps the
+        exchange; ``wait()`` (called by ``result`` and ``reset``) joins it."""
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return self
+        self.wait()
         world = dist.get_world_size(group)
         if self.owned:
             if world * self.owned[1] != self.n_segments or dist.get_rank(group) != self.owned[0] // self.owned[1]:
                 raise ValueError("owned blocks must follow the rank order of the group")
             k = self.owned[0] // self.owned[1]
             mine = self._flat[k * self._block_len:(k + 1) * self._block_len]
-            dist.all_gather_into_tensor(self._flat, mine, group=group)
-            return self
-        parts = [torch.empty_like(self._flat) for _ in range(world)]
-        dist.all_gather(parts, self._flat, group=group)
-        stacked = torch.stack(parts)
-        self._flat[:self._n_sum] = stacked[:, :self._n_sum].sum(dim=0, dtype=torch.int32)
-        self._flat[self._n_sum:] = stacked[:, self._n_sum:].amin(dim=0)
+            work = dist.all_gather_into_tensor(self._flat, mine, group=group, async_op=async_op)
+        else:
+            if self._gathered is None or self._gathered.shape[0] != world:
+                self._gathered = torch.empty((world, self._flat.numel()), dtype=torch.int32, device=self._flat.device)
+            work = dist.all_gather_into_tensor(self._gathered.view(-1), self._flat, group=group, async_op=async_op)
+        if async_op:
+            self._work = work
+        else:
+            self._finish()
+        return self
+
+    def _finish(self):
+        if not self.owned and self._gathered is not None:
+            self._flat[:self._n_sum] = self._gathered[:, :self._n_sum].sum(dim=0, dtype=torch.int32)
+            self._flat[self._n_sum:] = self._gathered[:, self._n_sum:].amin(dim=0)
+
+    def wait(self):
+        """Join a pending asynchronous ``combine`` (the current stream waits for the collective)."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+            self._finish()
         return self
 
     def result(self):
         """Per segment: (pattern uint8 [L] or None, frequency or None, bit_votes int [L], frames)."""
+        self.wait()
         bins = 1 << self.payload_len
         hist = self.hist.cpu().numpy().reshape(self.n_segments, bins)
         first = self.first_seen.cpu().numpy().reshape(self.n_segments, bins)

@@ -21,6 +21,7 @@ int launch_vote_counts(const uint32_t*, int, int, long long, int, int32_t*, cuda
 int launch_vote_finish(const int32_t*, int, int, long long, const int32_t*, uint8_t*, uint64_t*, cudaStream_t);
 int launch_pattern_hist(const uint64_t*, const int32_t*, const int32_t*, int, int, int, int, int32_t*, int32_t*, int32_t*,
                         int32_t*, cudaStream_t);
+int launch_vote_state_reset(int32_t*, long long, long long, cudaStream_t);
 int launch_dct8_masks(const void*, const b200wm_plane*, float*, float*, double*, cudaStream_t);
 int launch_dct8_embed(const void*, void*, const b200wm_plane*, const float*, const float*, const double*, const uint32_t*,
                       int, int, long long, const int32_t*, float, cudaStream_t);
@@ -164,6 +165,10 @@ B200WM_API int b200wm_pattern_hist(const uint64_t* packed, const int32_t* frame_
                         int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames, void* stream) {
     return launch_pattern_hist(packed, frame_segment, frame_order, order_offset, n_frames, payload_len, n_segments, hist,
                                first_seen, bit_votes, seg_frames, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_vote_state_reset(int32_t* state, int64_t n_zero, int64_t n_total, void* stream) {
+    return launch_vote_state_reset(state, n_zero, n_total, (cudaStream_t)stream);
 }
 
 B200WM_API int b200wm_bgr8_to_yuv32(const uint8_t* bgr, float* yuv, int64_t n_pixels, void* stream) {

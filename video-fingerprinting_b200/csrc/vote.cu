@@ -148,6 +148,22 @@ __global__ void __launch_bounds__(256) pattern_hist_kernel(const unsigned long l
         if ((p >> (L - 1 - j)) & 1ull) atomicAdd(&bit_votes[(long long)seg * L + j], 1);
 }
 
+// One launch that puts a vote state back to "nothing seen": zeros for the counters, INT32_MAX for first_seen.
+__global__ void __launch_bounds__(256) vote_state_reset_kernel(int32_t* __restrict__ state, long long n_zero, long long n_total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x)
+        state[i] = i < n_zero ? 0 : INT_MAX;
+}
+
+int launch_vote_state_reset(int32_t* state, long long n_zero, long long n_total, cudaStream_t stream) {
+    if (!state || n_zero < 0 || n_total < n_zero) return B200WM_ERR_INVALID;
+    if (n_total == 0) return B200WM_OK;
+    long long blocks = (n_total + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 1184) blocks = 1184;
+    vote_state_reset_kernel<<<(unsigned)blocks, 256, 0, stream>>>(state, n_zero, n_total);
+    B200WM_LAUNCH_CHECK("vote_state_reset_kernel");
+    return B200WM_OK;
+}
+
 int launch_pattern_hist(const uint64_t* packed, const int32_t* frame_segment, const int32_t* frame_order,
                         int order_offset, int n_frames, int payload_len, int n_segments, int32_t* hist,
                         int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames, cudaStream_t stream) {
