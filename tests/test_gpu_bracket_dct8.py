@@ -34,27 +34,53 @@ def _masks_oracle(lum):
     return coeffs[..., 0, 0] / 8, o_dct.texture_mask_from_coeffs(coeffs), o_dct.luminance_mask_from_dc(coeffs[..., 0, 0])
 
 
+def _frame_1080p(golden_dir):
+    """The reference's 1080p still is not shipped whole (fixtures hold a 384x640 crop): tile the crop to 1080p and
+    add seeded sensor-like noise so that the tiles are not copies of each other."""
+    crop = np.load(os.path.join(golden_dir, "frame63_crop.npz"))["bgr"]
+    reps = (-(-1080 // crop.shape[0]), -(-1920 // crop.shape[1]), 1)
+    tile = np.tile(crop, reps)[:1080, :1920].astype(np.float32)
+    return np.clip(np.rint(tile + np.random.RandomState(63).normal(0, 1.5, tile.shape)), 0, 255).astype(np.uint8)
+
+
+def _sources(golden_dir):
+    yield "frame63 crop", np.load(os.path.join(golden_dir, "frame63_crop.npz"))["bgr"]
+    yield "synthetic 128x192", synth.random_bgr(128, 192, 21)
+    yield "synthetic 100x132 (ragged)", synth.random_bgr(100, 132, 9)
+    yield "1080p (fixture tiled + noise)", _frame_1080p(golden_dir)
+
+
+def _explained(diff_blocks, ties, what, limit=5e-3):
+    """Every block in ``diff_blocks`` must carry one of the tie reasons; and ties may excuse only a small share."""
+    unexplained = diff_blocks & ~ties
+    assert not unexplained.any(), f"{what}: {int(unexplained.sum())} blocks differ without a float32 tie, e.g. {np.argwhere(unexplained)[:4].tolist()}"
+    assert diff_blocks.mean() < limit, f"{what}: {diff_blocks.mean():.2e} of the blocks differ (all ties, but too many)"
+    return int(diff_blocks.sum())
+
+
 def test_dct8_masks_vs_oracle(golden_dir):
+    """dct_encoder.py:41-102: block means within float32 rounding, frame sum, and the texture mask EQUAL to the
+    reference's wherever no comparison of its decision tree is a float32 tie (oracle/dct8.py:tie_blocks names them)."""
     from b200wm import ops
-    g = np.load(os.path.join(golden_dir, "frame63_crop.npz"))
-    for frame in (g["bgr"], synth.random_bgr(100, 132, 9), synth.random_bgr(64, 64, 3)):
+    for name, frame in _sources(golden_dir):
         yuv = bracket.to_yuv(frame)
         mean_o, tex_o, lum_o = _masks_oracle(yuv[:, :, 0])
         block_mean, tex, frame_sum = ops.dct8_masks(torch.from_numpy(yuv).to(DEV), channel=0)
         np.testing.assert_allclose(block_mean[0].cpu().numpy(), mean_o.reshape(-1), rtol=2e-6, atol=2e-5)
         np.testing.assert_allclose(float(frame_sum[0]), mean_o.astype(np.float64).sum(), rtol=1e-6)
         tex_g = tex[0].cpu().numpy().reshape(tex_o.shape)
-        agree = np.isclose(tex_g, tex_o, rtol=1e-5, atol=1e-6)
-        assert agree.mean() > 0.995, f"texture mask agreement {agree.mean()}"
+        differ = ~np.isclose(tex_g, tex_o, rtol=2e-5, atol=1e-6)        # the ramp 1 + 1.25 (eh - 290) / 1510 is continuous in eh
+        n = _explained(differ, o_dct.tie_blocks(yuv)["mask"], f"texture mask, {name}")
+        print(f"{name}: texture mask differs on {n} of {differ.size} blocks, all decision-tree ties")
 
 
-@pytest.mark.parametrize("source", ["frame63", "synthetic"])
+@pytest.mark.parametrize("source", ["frame63 crop", "synthetic 128x192", "synthetic 100x132 (ragged)", "1080p (fixture tiled + noise)"])
 def test_dct8_embed_extract_vs_oracle(golden_dir, source):
+    """DctEncoder.encode / DctDecoder.decode on the reference's float32 interleaved layout: marked channel within 2e-3
+    (float32) of the reference on EVERY block that is not a nameable float32 tie (mask decision, sign of a c21 below
+    noise, floor or rounding on a half-step), raw bits likewise, golden bit arrays of the reference itself, votes."""
     from b200wm import ops
-    if source == "frame63":
-        frame = np.load(os.path.join(golden_dir, "frame63_crop.npz"))["bgr"]
-    else:
-        frame = synth.random_bgr(128, 192, 21)
+    frame = dict(_sources(golden_dir))[source]
     yuv0 = bracket.to_yuv(frame)
     wm = o_pay.generate_wm(PAYLOAD, o_svd.wm_capacity(frame.shape), KEY)
     want = o_dct.encode(yuv0.copy(), wm)
@@ -64,27 +90,75 @@ def test_dct8_embed_extract_vs_oracle(golden_dir, source):
     ops.dct8_embed_(t, masks, packed, n, alpha=20, channel=1)
     got = t.cpu().numpy()
     assert np.array_equal(got[:, :, 0], yuv0[:, :, 0]) and np.array_equal(got[:, :, 2], yuv0[:, :, 2])
-    # Per-block agreement.  Where |c21| is below float32 noise its SIGN is decided by rounding inside
-    # cv2.dct, and the embedder multiplies by np.sign(c21) (dct_encoder.py:33-35): such blocks get
-    # +step or -step (or stay unmarked when cv2 returns exactly 0) - equally readable marks, no
-    # independent implementation can reproduce the choice.  Everywhere else the blocks must agree,
-    # up to the rare mask-threshold ties.
     by, bx = frame.shape[0] // 8, frame.shape[1] // 8
-    c21 = o_dct._dct_all(yuv0[:, :, 1])[..., 2, 1]
+    assert np.array_equal(got[by * 8:, :, 1], yuv0[by * 8:, :, 1]) and np.array_equal(got[:, bx * 8:, 1], yuv0[:, bx * 8:, 1])
+    ties = o_dct.tie_blocks(yuv0)
     err = np.abs(got[:by * 8, :bx * 8, 1] - want[:by * 8, :bx * 8, 1]).reshape(by, 8, bx, 8).max(axis=(1, 3))
-    solid = np.abs(c21) > 1e-3
-    agree = (err < 2e-3)
-    assert agree[solid].mean() > 0.995, f"block agreement {agree[solid].mean()} on {solid.sum()} blocks"
-    assert agree.mean() > 0.97, f"overall block agreement {agree.mean()}"
-    # extraction: our extractor on the reference's marked frame, and the reference's on ours
-    bits_ref = o_dct.decode(want.copy())
-    tw = torch.from_numpy(want).to(DEV)
-    raw, counts = ops.dct8_extract(tw, ops.dct8_masks(tw, channel=0), alpha=20, payload_len=8, channel=1)
-    bits = ops.unpack_bits(raw, bits_ref.size)
-    assert (bits == bits_ref).mean() > 0.995
-    assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), o_pay.degenerate(bits_ref, 8, KEY))
+    n_embed = _explained(err >= 2e-3, ties["mask"] | ties["sign"] | ties["floor"], f"embed, {source}", limit=6e-2)
+    # after the uint8 bracket (video/embedder.py:36-38) the frames agree within 1 LSB on those same blocks
+    d8 = np.abs(bracket.from_yuv(got.copy()).astype(np.int16) - bracket.from_yuv(want.copy())).max(axis=2)
+    d8 = d8[:by * 8, :bx * 8].reshape(by, 8, bx, 8).max(axis=(1, 3))
+    _explained(d8 > 1, ties["mask"] | ties["sign"] | ties["floor"], f"embed after the uint8 bracket, {source}", limit=6e-2)
+    # extraction: our extractor on the reference's marked frame (and on the clean one), against the reference's
+    for label, src in (("marked", want), ("clean", yuv0)):
+        bits_ref = o_dct.decode(src.copy())
+        ts = torch.from_numpy(src).to(DEV)
+        raw, counts = ops.dct8_extract(ts, ops.dct8_masks(ts, channel=0), alpha=20, payload_len=8, channel=1)
+        bits = ops.unpack_bits(raw, bits_ref.size)
+        t2 = o_dct.tie_blocks(src)
+        differ = np.zeros(by * bx, dtype=bool) | (bits[0, :by * bx] != bits_ref[0, :by * bx])
+        n_x = _explained(differ.reshape(by, bx), t2["mask"] | t2["round"], f"extract {label}, {source}", limit=1e-2)
+        assert not bits[0, by * bx:].any()
+        assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), o_pay.degenerate(bits_ref, 8, KEY))
+        assert counts[0].cpu().tolist() == [int(bits[0][i::8].sum()) for i in range(8)]
+        print(f"{source}: extract {label}: {n_x} of {by * bx} bits differ, all ties; embed: {n_embed} blocks differ, all ties")
     assert np.array_equal(o_pay.degenerate(o_dct.decode(got.copy()), 8, KEY), PAYLOAD)
-    assert counts[0].cpu().tolist() == [int(bits[0][i::8].sum()) for i in range(8)]
+    if source == "frame63 crop":        # the reference's own outputs (oracle/make_golden.py ran the reference itself)
+        g = np.load(os.path.join(golden_dir, "frame63_crop.npz"))
+        nb = int(g["dct8_nbits"])
+        ref_u8 = (frame.astype(np.int16) + g["dct8_marked_minus_src"]).astype(np.uint8)
+        for key, src in (("dct8_bits_clean", yuv0), ("dct8_bits_marked_f32", want), ("dct8_bits_marked_u8", bracket.to_yuv(ref_u8))):
+            ts = torch.from_numpy(src).to(DEV)
+            raw, _ = ops.dct8_extract(ts, ops.dct8_masks(ts, channel=0), alpha=20, channel=1)
+            gold = np.unpackbits(g[key])[:nb]
+            t2 = o_dct.tie_blocks(src)
+            differ = (ops.unpack_bits(raw, nb)[0, :by * bx] != gold[:by * bx]).reshape(by, bx)
+            _explained(differ, t2["mask"] | t2["round"], f"golden {key}", limit=1e-2)
+        h, w = g["dct8_marked_f32_ch1_window"].shape
+        werr = np.abs(got[:h, :w, 1] - g["dct8_marked_f32_ch1_window"]).reshape(h // 8, 8, w // 8, 8).max(axis=(1, 3))
+        _explained(werr >= 2e-3, (ties["mask"] | ties["sign"] | ties["floor"])[:h // 8, :w // 8], "golden marked window", limit=6e-2)
+
+
+def test_dct8_planar_u8_1080p_vs_oracle(golden_dir):
+    """The same pair on planar uint8 4:4:4 planes at 1080p (masks from Y, mark in U): marked plane within 1 LSB of
+    the reference flow (float YUV -> DctEncoder -> clip / around, video/embedder.py:37-38) on every block that is not
+    a nameable tie, raw bits of the marked plane likewise, identical votes."""
+    from b200wm import ops
+    frame = _frame_1080p(golden_dir)
+    yp, up = np.ascontiguousarray(frame[:, :, 1]), np.ascontiguousarray(frame[:, :, 0])
+    h, w = yp.shape
+    wm = o_pay.generate_wm(PAYLOAD, (1, h * w // 64), KEY)
+    packed, n = ops.pack_bits(wm[0], device=DEV)
+    yuv = np.zeros((h, w, 3), dtype=np.float32)
+    yuv[:, :, 0], yuv[:, :, 1] = yp, up
+    ties = o_dct.tie_blocks(yuv)
+    want = np.around(np.clip(o_dct.encode(yuv.copy(), wm)[:, :, 1], 0, 255)).astype(np.uint8)
+    ty, tu = torch.from_numpy(yp).to(DEV), torch.from_numpy(up.copy()).to(DEV)
+    masks = ops.dct8_masks(ty)
+    ops.dct8_embed_(tu, masks, packed, n, alpha=20)
+    got = tu.cpu().numpy()
+    by, bx = h // 8, w // 8
+    d = np.abs(got.astype(np.int16) - want).reshape(by, 8, bx, 8).max(axis=(1, 3))
+    n_embed = _explained(d > 1, ties["mask"] | ties["sign"] | ties["floor"], "planar u8 embed 1080p", limit=6e-2)   # tolerance: 1 LSB
+    yuv[:, :, 1] = got
+    bits_ref = o_dct.decode(yuv)
+    raw, counts = ops.dct8_extract(tu, masks, alpha=20, payload_len=8)
+    bits = ops.unpack_bits(raw, h * w // 64)
+    t2 = o_dct.tie_blocks(yuv)
+    n_x = _explained((bits[0] != bits_ref[0]).reshape(by, bx), t2["mask"] | t2["round"], "planar u8 extract 1080p", limit=1e-2)
+    assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), o_pay.degenerate(bits_ref, 8, KEY))
+    assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), PAYLOAD)
+    print(f"1080p planar u8: {n_embed} blocks off by more than 1 LSB and {n_x} bits differ of {by * bx}, all ties")
 
 
 def test_dct8_uint8_planes_fast_path_vs_generic_and_oracle():
