@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kThreads, kMode == 0 ? 8 : 1) dwtsvd_embed_ker
         const uint8_t* p = pl.src + off + (long long)tx * 8 * es * 4;
         uint8_t* o = pl.dst + off + (long long)tx * 8 * es * 4;
         load_tile_generic<float>(p, pl.pitch, es, S);
-        embed_deltas<false>(S, bit, em.scale, em.inv_scale, 0.0f, D, nullptr, [&]() { return flat_probe_global<float>(p, pl.pitch, es); });
+        embed_deltas<false, 3>(S, bit, em.scale, em.inv_scale, 0.0f, D, nullptr, [&]() { return flat_probe_global<float>(p, pl.pitch, es); });
 #pragma unroll
         for (int y = 0; y < 8; ++y) {
             const float* pr = reinterpret_cast<const float*>(row_ptr(p, y, pl.pitch));
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads) dwtsvd_extract_kernel(PlaneArgs pl, 
             load_tile_generic<float>(pl.src + off + (long long)tx * 8 * pl.elem_stride * 4, pl.pitch, pl.elem_stride, S);
         }
         float sigma;
-        bit = extract_bit(S, ex.scale, ex.inv_scale, sigma, [&]() {
+        bit = extract_bit<kMode == 2 ? 3 : 0>(S, ex.scale, ex.inv_scale, sigma, [&]() {
             if (kMode == 2) return flat_probe_global<float>(pl.src + off + (long long)tx * 8 * pl.elem_stride * 4, pl.pitch, pl.elem_stride);
             return flat_probe_global<uint8_t>(pl.src + off + (long long)tx * 8 * (kMode == 0 ? 1 : pl.elem_stride), pl.pitch,
                                               kMode == 0 ? 1 : pl.elem_stride);

@@ -178,7 +178,8 @@ __device__ __forceinline__ void load_tile_generic(const uint8_t* p, unsigned pit
 // Per-sample increment of each 2x2 of the tile for watermark bit `bit`: D[4*i+j] = (S'-S)[i][j]/4.
 // kStash: park S in shared memory while the eigen-iteration runs (4 STS.128 + 4 LDS.128 per
 // thread) instead of letting the compiler rebuild it from the pixel bytes under register pressure.
-template <bool kStash, typename Probe>
+// kDeep: straight-line squarings of the eigen-iteration (svd4.cuh): 0 for uint8 luma planes, 3 for float / chroma input
+template <bool kStash, int kDeep = 0, typename Probe>
 __device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scale, float inv_scale,
                                              float bias, float (&D)[16], float4* stash, Probe probe) {
     float v[4];
@@ -189,7 +190,7 @@ __device__ __forceinline__ void embed_deltas(float (&S)[16], int bit, float scal
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(stash + i * kThreads)),
                          "f"(S[4 * i]), "f"(S[4 * i + 1]), "f"(S[4 * i + 2]), "f"(S[4 * i + 3]) : "memory");
     }
-    float sigma = 0.5f * top_singular<true>(S, v, zero, maybe_flat);   // sigma_0 of the LL block
+    float sigma = 0.5f * top_singular<true, kDeep>(S, v, zero, maybe_flat);   // sigma_0 of the LL block
     float q, rem;
     floor_divmod(sigma, scale, inv_scale, q, rem);
     if (maybe_flat && on_boundary<false>(sigma, rem, scale)) {
@@ -266,11 +267,11 @@ __device__ __forceinline__ void embed_copy_deltas(const BlockPair& bp, int bit, 
     }
 }
 
-template <typename Probe>
+template <int kDeep = 0, typename Probe>
 __device__ __forceinline__ int extract_bit(const float (&S)[16], float scale, float inv_scale, float& sigma, Probe probe) {
     float v[4];
     bool zero, maybe_flat;
-    sigma = 0.5f * top_singular<false>(S, v, zero, maybe_flat);
+    sigma = 0.5f * top_singular<false, kDeep>(S, v, zero, maybe_flat);
     float q, rem;
     floor_divmod(sigma, scale, inv_scale, q, rem);
     if (maybe_flat && on_boundary<true>(sigma, rem, scale)) {

@@ -57,30 +57,116 @@ __device__ __forceinline__ void load_row24(const uint8_t* p, unsigned (&w)[6]) {
     }
 }
 
-__device__ __forceinline__ float byte_of(const unsigned (&w)[6], int i) {
-    return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);       // compiles to one I2F with a byte selector
+// byte i of a row as the float 2^23 + byte: PRMT drops it into the mantissa of 2^23 (exact); the 2^23 is removed by a
+// packed FADD2 on two pixels at once.  An I2F per byte would put 384 conversions per tile on the quarter-rate
+// conversion pipe.
+__device__ __forceinline__ float biased_of(const unsigned (&w)[6], int i) {
+    return __uint_as_float(__byte_perm(w[i >> 2], 0x4B000000u, 0x7650u | (unsigned)(i & 3)));
+}
+// Two pixels per instruction (FFMA2 / FADD2 / FMUL2): lane .x and lane .y are different pixels, every operation is the
+// scalar formula's operation in the scalar formula's order, so the values are OpenCV's float path bit for bit.
+struct Yuv2 { f2 y, u, v; };
+__device__ __forceinline__ Yuv2 px_to_yuv2(f2 b0, f2 b1, f2 b2) {        // b*: 2^23 + byte
+    const f2 unbias = bc2(-8388608.0f);
+    const f2 c0 = add2(b0, unbias), c1 = add2(b1, unbias), c2 = add2(b2, unbias);
+    Yuv2 o;
+    o.y = fma2(c0, bc2(0.114f), fma2(c1, bc2(0.587f), mul2(c2, bc2(0.299f))));
+    o.u = fma2(fma2(o.y, bc2(-1.0f), c0), bc2(0.492f), bc2(0.5f));      // (c0 - y) * 0.492 + 0.5; y * -1 + c0 == c0 - y exactly
+    o.v = fma2(fma2(o.y, bc2(-1.0f), c2), bc2(0.877f), bc2(0.5f));
+    return o;
 }
 
 // 24 colour values of a row -> 24 bytes: clip(., 0, 255) then round-half-even (video/embedder.py:37-38) equals
 // round-half-even then clamp; adding 1.5 * 2^23 rounds and leaves the integer in the low mantissa bits, which
 // are packed as int16 lanes, clamped by one DPX instruction per two values and narrowed to bytes.
 __device__ __forceinline__ void pack_row24(const float (&c)[24], unsigned (&out)[6]) {
+    const f2 bias = bc2(12582912.0f);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        const unsigned b0 = __float_as_uint(c[4 * k] + 12582912.0f), b1 = __float_as_uint(c[4 * k + 1] + 12582912.0f);
-        const unsigned b2 = __float_as_uint(c[4 * k + 2] + 12582912.0f), b3 = __float_as_uint(c[4 * k + 3] + 12582912.0f);
-        const unsigned e = __viaddmin_s16x2_relu(__byte_perm(b0, b2, 0x5410), 0u, 0x00FF00FFu);
-        const unsigned o = __viaddmin_s16x2_relu(__byte_perm(b1, b3, 0x5410), 0u, 0x00FF00FFu);
+        const f2 lo = add2(make_float2(c[4 * k], c[4 * k + 1]), bias), hi = add2(make_float2(c[4 * k + 2], c[4 * k + 3]), bias);
+        const unsigned e = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(lo.x), __float_as_uint(hi.x), 0x5410), 0u, 0x00FF00FFu);
+        const unsigned o = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(lo.y), __float_as_uint(hi.y), 0x5410), 0u, 0x00FF00FFu);
         out[k] = __byte_perm(e, o, 0x6240);
     }
 }
 
+// The four 2x2 sums of one LL row (pixel rows 2i and 2i+1 of the tile) for the channels in kMask.  Packed lanes are
+// (row 2i, row 2i+1) of the same pixel column, so a 2x2 is (left + right) in both lanes, then lane .x + lane .y:
+// (top-left + top-right) + (bottom-left + bottom-right) like the scalar loader of dwtsvd_tile.cuh.
+template <bool kAligned, int kMask>
+__device__ __forceinline__ void ll_row_sums(const uint8_t* p, unsigned pitch, float (&s)[3][4]) {
+    unsigned r0[6], r1[6];
+    load_row24<kAligned>(p, r0);
+    load_row24<kAligned>(p + pitch, r1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        Yuv2 q[2];
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int px = 2 * j + dx;
+            q[dx] = px_to_yuv2(make_float2(biased_of(r0, 3 * px), biased_of(r1, 3 * px)),
+                               make_float2(biased_of(r0, 3 * px + 1), biased_of(r1, 3 * px + 1)),
+                               make_float2(biased_of(r0, 3 * px + 2), biased_of(r1, 3 * px + 2)));
+        }
+        if (kMask & 1) { const f2 t = add2(q[0].y, q[1].y); s[0][j] = t.x + t.y; }
+        if (kMask & 2) { const f2 t = add2(q[0].u, q[1].u); s[1][j] = t.x + t.y; }
+        if (kMask & 4) { const f2 t = add2(q[0].v, q[1].v); s[2][j] = t.x + t.y; }
+    }
+}
+
+// G += s s^T for one row of the block, packed upper-triangular: row 0 first, then rows 1..3 - the accumulation order
+// of gram4() (fma(a, b, 0) rounds like a * b), so the eigen-solver sees the Gram matrix it would get from the whole block.
+__device__ __forceinline__ void gram_add_row(const float (&s)[4], float (&G)[10]) {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j, ++k) G[k] = fmaf(s[i], s[j], G[k]);
+}
+
+// What embed_deltas() of dwtsvd_tile.cuh derives from a block, without the block: the increment of the 2x2 (i, j)
+// is  flat ? flat_inc : (t * (S_row_i . v)) * v[j].
+struct EmbedFactors {
+    float v[4], t, flat_inc;
+    bool flat;              // all-zero block: svd(0) = (I, 0, I), the same increment everywhere
+};
+
+template <typename Probe>
+__device__ __forceinline__ void embed_factors(float (&G)[10], int bit, float scale, float inv_scale, EmbedFactors& f, Probe probe) {
+    bool maybe_flat;
+    float sigma = 0.5f * top_singular_gram<true, 3>(G, f.v, f.flat, maybe_flat);
+    float q, rem;
+    floor_divmod(sigma, scale, inv_scale, q, rem);
+    if (maybe_flat && on_boundary<false>(sigma, rem, scale)) {
+        const float flat = probe();
+        if (flat == flat) {
+            sigma = flat_sigma_ref(flat);
+            floor_divmod(sigma, scale, inv_scale, q, rem);
+        }
+    }
+    const float target = (q + 0.25f + 0.5f * (float)bit) * scale;
+    f.flat_inc = target * 0.125f;
+    f.t = 0.25f * ((target - sigma) / sigma);
+}
+
 // kMask: bit c set = YUV channel c is marked (scale[c] > 0); compile-time so that unmarked channels
 // cost neither registers nor instructions (the reference default, scales=[0,15,0], is kMask = 2).
+//
+// Two rolled passes over the four LL rows of the tile (code that fits the instruction cache: the fully unrolled
+// predecessor was 107 KB of SASS and stalled on instruction fetch more than on anything else, profiles/r02_fused_rgb.md):
+//   pass A  convert two pixel rows, form the row's four 2x2 sums per marked channel, park them in shared memory and
+//           add their outer product to the Gram matrix;
+//   solve   sigma_0, v_0 and the quantisation target per marked channel from the Gram matrix alone;
+//   pass B  convert the two pixel rows again (L1 hits), add the row's increments in YUV space, convert back, clip,
+//           round, store.
+constexpr int kRgbThreads = 128;
+
 template <bool kAligned, int kMask>
-__global__ void __launch_bounds__(128, 4) dwtsvd_embed_rgb8_kernel(RgbArgs a, EmbedArgs em, TileGeom g, int frame0) {
+__global__ void __launch_bounds__(kRgbThreads, 4) dwtsvd_embed_rgb8_kernel(RgbArgs a, EmbedArgs em, TileGeom g, int frame0) {
+    constexpr int kCh = (kMask & 1) + ((kMask >> 1) & 1) + ((kMask >> 2) & 1);
+    __shared__ float4 s_rows[kCh][4][kRgbThreads];
     const int frame = frame0 + blockIdx.y;
-    const unsigned c = blockIdx.x * 128 + threadIdx.x;
+    const unsigned c = blockIdx.x * kRgbThreads + threadIdx.x;
     if (c >= (unsigned)g.n_tiles) return;
     const unsigned ty = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
     const unsigned tx = c - ty * g.tiles_x;
@@ -88,71 +174,82 @@ __global__ void __launch_bounds__(128, 4) dwtsvd_embed_rgb8_kernel(RgbArgs a, Em
     const int bit = (em.wm[(long long)row * em.wm_words + (c >> 5)] >> (c & 31)) & 1;
     const long long off = frame * a.frame_stride + (unsigned long long)(ty * 8) * a.pitch + tx * 24;
 
-    // Pass A: 2x2 sums of the marked channels.  The 192 source bytes are NOT kept in registers across
-    // the eigen-iteration; pass B re-reads them row by row (L1 hits).
-    float S[3][16];
+    float G[3][10];
 #pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) G[ch][k] = 0.0f;
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) {
-        unsigned r0[6], r1[6];
-        load_row24<kAligned>(a.src + off + (unsigned long long)(2 * i) * a.pitch, r0);
-        load_row24<kAligned>(a.src + off + (unsigned long long)(2 * i + 1) * a.pitch, r1);
+        float s[3][4];
+        ll_row_sums<kAligned, kMask>(a.src + off + (unsigned long long)(2 * i) * a.pitch, a.pitch, s);
+        int slot = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float y[4], u[4], v[4];
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                const int px = 2 * j + dx;
-                px_to_yuv(byte_of(r0, 3 * px), byte_of(r0, 3 * px + 1), byte_of(r0, 3 * px + 2), y[dx], u[dx], v[dx]);
-                px_to_yuv(byte_of(r1, 3 * px), byte_of(r1, 3 * px + 1), byte_of(r1, 3 * px + 2), y[2 + dx], u[2 + dx], v[2 + dx]);
+        for (int ch = 0; ch < 3; ++ch)
+            if (kMask & (1 << ch)) {
+                gram_add_row(s[ch], G[ch]);
+                s_rows[slot++][i][threadIdx.x] = make_float4(s[ch][0], s[ch][1], s[ch][2], s[ch][3]);
             }
-            if (kMask & 1) S[0][4 * i + j] = (y[0] + y[1]) + (y[2] + y[3]);
-            if (kMask & 2) S[1][4 * i + j] = (u[0] + u[1]) + (u[2] + u[3]);
-            if (kMask & 4) S[2][4 * i + j] = (v[0] + v[1]) + (v[2] + v[3]);
-        }
     }
-    float D[3][16];
+    EmbedFactors f[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
         if (kMask & (1 << ch))
-            embed_deltas<false>(S[ch], bit, a.scale[ch], 1.0f / a.scale[ch], 0.0f, D[ch], nullptr,
-                                [&]() { return flat_probe_rgb(a.src + off, a.pitch, ch); });
+            embed_factors(G[ch], bit, a.scale[ch], 1.0f / a.scale[ch], f[ch], [&]() { return flat_probe_rgb(a.src + off, a.pitch, ch); });
 
-    // Pass B: convert again, add the increments in YUV space, convert back, clip, round, store.
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        float d[3][4];                       // increments of the four 2x2 of this LL row
+        int slot = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        unsigned raw[6];
-        load_row24<kAligned>(a.src + off + (unsigned long long)r * a.pitch, raw);
-        float cv[24];
+        for (int ch = 0; ch < 3; ++ch)
+            if (kMask & (1 << ch)) {
+                const float4 sr = s_rows[slot++][i][threadIdx.x];
+                const float sv = fmaf(sr.w, f[ch].v[3], fmaf(sr.z, f[ch].v[2], fmaf(sr.y, f[ch].v[1], sr.x * f[ch].v[0])));
+                const float ai = f[ch].t * sv;
 #pragma unroll
-        for (int px = 0; px < 8; ++px) {
-            float y, u, v;
-            px_to_yuv(byte_of(raw, 3 * px), byte_of(raw, 3 * px + 1), byte_of(raw, 3 * px + 2), y, u, v);
-            const int k = 4 * (r >> 1) + (px >> 1);
-            if (kMask & 1) y += D[0][k];
-            if (kMask & 2) u += D[1][k];
-            if (kMask & 4) v += D[2][k];
-            const float du = u - 0.5f, dv = v - 0.5f;
-            cv[3 * px] = fmaf(du, 2.032f, y);
-            cv[3 * px + 1] = fmaf(dv, -0.581f, fmaf(du, -0.395f, y));
-            cv[3 * px + 2] = fmaf(dv, 1.14f, y);
-        }
-        unsigned out[6];
-        pack_row24(cv, out);
-        uint8_t* o = a.dst + off + (unsigned long long)r * a.pitch;
-        if (kAligned) {
-            uint2* q = reinterpret_cast<uint2*>(o);
-            q[0] = make_uint2(out[0], out[1]); q[1] = make_uint2(out[2], out[3]); q[2] = make_uint2(out[4], out[5]);
-        } else {
+                for (int j = 0; j < 4; ++j) d[ch][j] = f[ch].flat ? f[ch].flat_inc : ai * f[ch].v[j];
+            }
 #pragma unroll
-            for (int k = 0; k < 24; ++k) o[k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
+        for (int rr = 0; rr < 2; ++rr) {
+            const unsigned long long ro = (unsigned long long)(2 * i + rr) * a.pitch;
+            unsigned raw[6];
+            load_row24<kAligned>(a.src + off + ro, raw);
+            float cv[24];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {         // lanes = pixels 2j and 2j+1 of this row: they share the increment of their 2x2
+                const int p0 = 2 * j, p1 = 2 * j + 1;
+                Yuv2 q = px_to_yuv2(make_float2(biased_of(raw, 3 * p0), biased_of(raw, 3 * p1)),
+                                    make_float2(biased_of(raw, 3 * p0 + 1), biased_of(raw, 3 * p1 + 1)),
+                                    make_float2(biased_of(raw, 3 * p0 + 2), biased_of(raw, 3 * p1 + 2)));
+                if (kMask & 1) q.y = add2(q.y, bc2(d[0][j]));
+                if (kMask & 2) q.u = add2(q.u, bc2(d[1][j]));
+                if (kMask & 4) q.v = add2(q.v, bc2(d[2][j]));
+                const f2 du = add2(q.u, bc2(-0.5f)), dv = add2(q.v, bc2(-0.5f));
+                const f2 o0 = fma2(du, bc2(2.032f), q.y);
+                const f2 o1 = fma2(dv, bc2(-0.581f), fma2(du, bc2(-0.395f), q.y));
+                const f2 o2 = fma2(dv, bc2(1.14f), q.y);
+                cv[3 * p0] = o0.x; cv[3 * p0 + 1] = o1.x; cv[3 * p0 + 2] = o2.x;
+                cv[3 * p1] = o0.y; cv[3 * p1 + 1] = o1.y; cv[3 * p1 + 2] = o2.y;
+            }
+            unsigned out[6];
+            pack_row24(cv, out);
+            uint8_t* o = a.dst + off + ro;
+            if (kAligned) {
+                uint2* q = reinterpret_cast<uint2*>(o);
+                q[0] = make_uint2(out[0], out[1]); q[1] = make_uint2(out[2], out[3]); q[2] = make_uint2(out[4], out[5]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 24; ++k) o[k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
+            }
         }
     }
 }
 
-template <bool kAligned>
-__global__ void __launch_bounds__(128) dwtsvd_extract_rgb8_kernel(RgbArgs a, int channel, ExtractArgs ex, TileGeom g, int frame0) {
+template <bool kAligned, int kChannel>      // kChannel: the YUV channel that is read (compile time: the two others cost nothing)
+__global__ void __launch_bounds__(kRgbThreads) dwtsvd_extract_rgb8_kernel(RgbArgs a, ExtractArgs ex, TileGeom g, int frame0) {
     const int frame = frame0 + blockIdx.y;
-    const unsigned c = blockIdx.x * 128 + threadIdx.x;
+    const unsigned c = blockIdx.x * kRgbThreads + threadIdx.x;
     const unsigned word = c >> 5;
     const bool live = word < (unsigned)g.words;
     int bit = 0;
@@ -160,29 +257,27 @@ __global__ void __launch_bounds__(128) dwtsvd_extract_rgb8_kernel(RgbArgs a, int
         const unsigned ty = (unsigned)(((unsigned long long)c * g.div_magic) >> 40);
         const unsigned tx = c - ty * g.tiles_x;
         const long long off = frame * a.frame_stride + (unsigned long long)(ty * 8) * a.pitch + tx * 24;
-        float S[16];
+        float G[10];
 #pragma unroll
+        for (int k = 0; k < 10; ++k) G[k] = 0.0f;
+#pragma unroll      // 4 x 330 instructions: small enough for the instruction cache, and the loads of all rows are in flight together
         for (int i = 0; i < 4; ++i) {
-            unsigned r0[6], r1[6];
-            load_row24<kAligned>(a.src + off + (unsigned long long)(2 * i) * a.pitch, r0);
-            load_row24<kAligned>(a.src + off + (unsigned long long)(2 * i + 1) * a.pitch, r1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float q[4];
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const int px = 2 * j + dx;
-                    float y, u, v;
-                    px_to_yuv(byte_of(r0, 3 * px), byte_of(r0, 3 * px + 1), byte_of(r0, 3 * px + 2), y, u, v);
-                    q[dx] = channel == 0 ? y : (channel == 1 ? u : v);
-                    px_to_yuv(byte_of(r1, 3 * px), byte_of(r1, 3 * px + 1), byte_of(r1, 3 * px + 2), y, u, v);
-                    q[2 + dx] = channel == 0 ? y : (channel == 1 ? u : v);
-                }
-                S[4 * i + j] = (q[0] + q[1]) + (q[2] + q[3]);
+            float s[3][4];
+            ll_row_sums<kAligned, 1 << kChannel>(a.src + off + (unsigned long long)(2 * i) * a.pitch, a.pitch, s);
+            gram_add_row(s[kChannel], G);
+        }
+        float v[4];
+        bool zero, maybe_flat;
+        float sigma = 0.5f * top_singular_gram<false, 3>(G, v, zero, maybe_flat), q, rem;
+        floor_divmod(sigma, ex.scale, ex.inv_scale, q, rem);
+        if (maybe_flat && on_boundary<true>(sigma, rem, ex.scale)) {
+            const float flat = flat_probe_rgb(a.src + off, a.pitch, kChannel);
+            if (flat == flat) {
+                sigma = flat_sigma_ref(flat);
+                floor_divmod(sigma, ex.scale, ex.inv_scale, q, rem);
             }
         }
-        float sigma;
-        bit = extract_bit(S, ex.scale, ex.inv_scale, sigma, [&]() { return flat_probe_rgb(a.src + off, a.pitch, channel); });
+        bit = rem > 0.5f * ex.scale ? 1 : 0;
     }
     const unsigned ballot = __ballot_sync(0xFFFFFFFFu, bit);
     const unsigned lane = threadIdx.x & 31;
@@ -225,8 +320,8 @@ int launch_embed_rgb8(const uint8_t* src, uint8_t* dst, int n_frames, int height
         const dim3 grid(gx, (unsigned)((n_frames - f0) < 65535 ? (n_frames - f0) : 65535));
 #define B200WM_RGB_CASE(M)                                                                          \
     case M:                                                                                         \
-        if (aligned) dwtsvd_embed_rgb8_kernel<true, M><<<grid, 128, 0, stream>>>(a, ea, g, f0);      \
-        else dwtsvd_embed_rgb8_kernel<false, M><<<grid, 128, 0, stream>>>(a, ea, g, f0);             \
+        if (aligned) dwtsvd_embed_rgb8_kernel<true, M><<<grid, kRgbThreads, 0, stream>>>(a, ea, g, f0);  \
+        else dwtsvd_embed_rgb8_kernel<false, M><<<grid, kRgbThreads, 0, stream>>>(a, ea, g, f0);         \
         break;
         switch (mask) {
             B200WM_RGB_CASE(1) B200WM_RGB_CASE(2) B200WM_RGB_CASE(3) B200WM_RGB_CASE(4)
@@ -258,8 +353,13 @@ int launch_extract_rgb8(const uint8_t* src, int n_frames, int height, int width,
         const unsigned gx = ((unsigned)g.words * 32 + 127) / 128;
         for (int f0 = 0; f0 < n_frames; f0 += 65535) {
             const dim3 grid(gx, (unsigned)((n_frames - f0) < 65535 ? (n_frames - f0) : 65535));
-            if (aligned) dwtsvd_extract_rgb8_kernel<true><<<grid, 128, 0, stream>>>(a, channel, xa, g, f0);
-            else dwtsvd_extract_rgb8_kernel<false><<<grid, 128, 0, stream>>>(a, channel, xa, g, f0);
+#define B200WM_RGB_X(CH)                                                                              \
+    case CH:                                                                                         \
+        if (aligned) dwtsvd_extract_rgb8_kernel<true, CH><<<grid, 128, 0, stream>>>(a, xa, g, f0);    \
+        else dwtsvd_extract_rgb8_kernel<false, CH><<<grid, 128, 0, stream>>>(a, xa, g, f0);           \
+        break;
+            switch (channel) { B200WM_RGB_X(0) B200WM_RGB_X(1) B200WM_RGB_X(2) }
+#undef B200WM_RGB_X
             B200WM_LAUNCH_CHECK("dwtsvd_extract_rgb8_kernel");
         }
     }
