@@ -211,7 +211,7 @@ B200WM_API int b200wm_vote_finish(const int32_t* pos_counts, int32_t n_frames, i
  * Cross-frame pattern vote, device half (tests/segment_mark_detect_hls.py:144-155):
  * histogram of per-frame patterns per segment plus what is needed to reproduce
  * Counter.most_common(1) exactly (ties -> pattern seen first) after an
- * all-reduce across GPUs.  payload_len <= 16.
+ * exchange across GPUs (an all-gather, b200wm/vote.py).  payload_len <= 16.
  * frame_segment [n_frames] (nullable -> segment 0); frame_order [n_frames]
  * (nullable -> order_offset + f): global position of each frame in its segment.
  * hist       [n_segments, 2^payload_len] int32, accumulated (caller zeroes)

@@ -53,6 +53,10 @@ __device__ __forceinline__ void load_rows_u8(const uint8_t* p, long long pitch, 
     for (int y = 0; y < 8; ++y) rows[y] = ldg_stream_u2(p + y * pitch);
 }
 template <int kByte>
+__device__ __forceinline__ float mid_biased_byte(unsigned w) {      // 32768 + byte: [0x47][0x00][byte][0x00]
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404 | (kByte << 4)));
+}
+template <int kByte>
 __device__ __forceinline__ float biased_byte(unsigned w) {
     return __uint_as_float(__byte_perm(w, kBiasBits, 0x7640 | kByte));
 }
@@ -147,15 +151,22 @@ __global__ void __launch_bounds__(kDctThreads, kVec ? B200WM_DCT_MASKS_MIN_CTAS 
                            (long long)bx * 8 * pl.elem_stride * (long long)sizeof(T);
         float b[64];
         if (kVec) {
+            // bytes into mantissa bits 8..15 of 2^15: value 32768 + sample, exact, with eight spare low bits so that
+            // the sums of eight such values are exact too; the row transform removes the bias (dct8.cuh)
             uint2 rows[8];
             load_rows_u8(p, pl.pitch, rows);
-            biased_block(rows, b);
 #pragma unroll
-            for (int k = 0; k < 64; ++k) b[k] -= kBias;
+            for (int y = 0; y < 8; ++y) {
+                b[8 * y + 0] = mid_biased_byte<0>(rows[y].x); b[8 * y + 1] = mid_biased_byte<1>(rows[y].x);
+                b[8 * y + 2] = mid_biased_byte<2>(rows[y].x); b[8 * y + 3] = mid_biased_byte<3>(rows[y].x);
+                b[8 * y + 4] = mid_biased_byte<0>(rows[y].y); b[8 * y + 5] = mid_biased_byte<1>(rows[y].y);
+                b[8 * y + 6] = mid_biased_byte<2>(rows[y].y); b[8 * y + 7] = mid_biased_byte<3>(rows[y].y);
+            }
+            dct8x8<8 * 32768>(b);
         } else {
             load_block<T>(p, pl.pitch, pl.elem_stride, b);
+            dct8x8(b);
         }
-        dct8x8(b);
         const float mean = b[0] * 0.125f;                  // mask[i][j] = coeffs[0][0]; mask /= 8
         const long long o = (long long)frame * g.nb + c;
         block_mean[o] = mean;

@@ -14,12 +14,17 @@ namespace b200wm {
 #define C7 0.19509032201612825f
 
 // Orthonormal 8-point DCT-II in place: X_k = a_k sum_n x_n cos((2n+1) k pi / 16), a_0 = 1/sqrt(8), a_k = 1/2.
+// kBias8: the inputs are integers that all carry the same additive bias B (bytes dropped into a float's mantissa by
+// PRMT, no conversion instruction) with kBias8 = 8 * B and every partial sum still exact in float32.  Every term
+// but the DC one is built from differences, in which B cancels exactly; the DC term removes 8 * B from the exact
+// integer sum before its only rounding - the outputs are bit-identical to the unbiased transform's.
+template <int kBias8 = 0>
 __device__ __forceinline__ void dct8_1d(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
                                         float& x7) {
     const float s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
     const float d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
     const float e0 = s0 + s3, e1 = s1 + s2, e2 = s1 - s2, e3 = s0 - s3;
-    x0 = (e0 + e1) * (0.5f * C4);
+    x0 = (kBias8 ? (e0 + e1) - (float)kBias8 : (e0 + e1)) * (0.5f * C4);
     x4 = (e0 - e1) * (0.5f * C4);
     x2 = fmaf(e3, 0.5f * C2, e2 * (0.5f * C6));
     x6 = fmaf(e3, 0.5f * C6, e2 * (-0.5f * C2));
@@ -47,10 +52,11 @@ __device__ __forceinline__ void idct8_1d(float& x0, float& x1, float& x2, float&
 }
 
 // 2-D transforms of an 8x8 block held in registers (row-major b[8*y+x]).
+template <int kBias8 = 0>
 __device__ __forceinline__ void dct8x8(float (&b)[64]) {
 #pragma unroll
     for (int y = 0; y < 8; ++y)
-        dct8_1d(b[8 * y], b[8 * y + 1], b[8 * y + 2], b[8 * y + 3], b[8 * y + 4], b[8 * y + 5], b[8 * y + 6], b[8 * y + 7]);
+        dct8_1d<kBias8>(b[8 * y], b[8 * y + 1], b[8 * y + 2], b[8 * y + 3], b[8 * y + 4], b[8 * y + 5], b[8 * y + 6], b[8 * y + 7]);
 #pragma unroll
     for (int x = 0; x < 8; ++x) dct8_1d(b[x], b[8 + x], b[16 + x], b[24 + x], b[32 + x], b[40 + x], b[48 + x], b[56 + x]);
 }

@@ -17,6 +17,7 @@
 // Memory: every sample of the plane is read exactly once (extract) or read once and written
 // once (embed) with 64-bit accesses that a warp coalesces into full 256-byte row segments;
 // algorithmic bytes per frame are W*H (extract) and 2*W*H (embed), see DESIGN.md.
+#include <atomic>
 #include "common.cuh"
 #include "svd4.cuh"
 #include "dwtsvd_tile.cuh"
@@ -246,9 +247,9 @@ int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, 
 
 // Path selection: 0 = automatic (TMA when the plane qualifies), 1 = force the LDG kernels.
 // Set through b200wm_set_path() for A/B measurements; results are identical either way.
-static int g_path = 0;
-void set_path(int p) { g_path = p; }
-int get_path() { return g_path; }
+static std::atomic<int> g_path{0};      // a measurement switch, read once per launch; results do not depend on it
+void set_path(int p) { g_path.store(p, std::memory_order_relaxed); }
+int get_path() { return g_path.load(std::memory_order_relaxed); }
 
 static int plane_mode(const void* a, const void* b, const b200wm_plane* pl) {
     if (pl->dtype == B200WM_F32) return 2;
@@ -279,7 +280,7 @@ int launch_dwtsvd_embed(const void* src, void* dst, const b200wm_plane* pl, cons
     if ((uintptr_t)src % 4 && pl->dtype == B200WM_F32) return B200WM_ERR_INVALID;
     PlaneArgs pa{(const uint8_t*)src, (uint8_t*)dst, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
     EmbedArgs ea{wm, frame_row, n_wm_rows, wm_words, scale, 1.0f / scale};
-    if (g_path == 0 && tma_eligible(src, dst, pl, g)) return launch_dwtsvd_embed_tma(src, dst, pl, g, ea, stream);
+    if (get_path() == 0 && tma_eligible(src, dst, pl, g)) return launch_dwtsvd_embed_tma(src, dst, pl, g, ea, stream);
     const int mode = plane_mode(src, dst, pl);
     const unsigned gx = (g.n_tiles + kThreads - 1) / kThreads;
     for (int f0 = 0; f0 < pl->n_frames; f0 += 65535) {
@@ -335,7 +336,7 @@ int launch_dwtsvd_extract(const void* src, const b200wm_plane* pl, float scale, 
     } else if (g.words > 0) {
         PlaneArgs pa{(const uint8_t*)src, nullptr, pl->frame_stride_bytes, (unsigned)pl->pitch_bytes, pl->elem_stride};
         ExtractArgs xa{raw_bits, fused ? pos_counts : nullptr, sigma, payload_len, fused ? every_mask(payload_len) : 0u, scale, 1.0f / scale};
-        if (g_path == 0 && !sigma && tma_eligible(src, src, pl, g)) {
+        if (get_path() == 0 && !sigma && tma_eligible(src, src, pl, g)) {
             // strips OR their bits into the packed words; surplus words must read 0
             B200WM_CUDA_TRY(cudaMemsetAsync(raw_bits, 0, sizeof(uint32_t) * (size_t)pl->n_frames * g.words, stream));
             rc = launch_dwtsvd_extract_tma(src, pl, g, xa, stream);

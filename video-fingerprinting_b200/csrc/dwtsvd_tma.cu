@@ -39,6 +39,7 @@
 // per row, base and frame stride multiples of 16 bytes, and either tight rows of at most 256 tiles (any
 // parity) or 16-byte aligned rows with an even number of tiles; rows of 129..183 tiles are left to the
 // vectorised-load kernels, which measured faster there.
+#include <mutex>
 #include "common.cuh"
 #include "svd4.cuh"
 #include "dwtsvd_tile.cuh"
@@ -47,8 +48,6 @@ namespace b200wm {
 
 constexpr int kStripThreads = 128;                 // consumer threads: two 8x8 tiles each (t and t + half)
 constexpr int kMaxStripTiles = 2 * kStripThreads;
-constexpr int kConsumerWarps = kStripThreads / 32;
-constexpr int kCtaThreads = kStripThreads + 32;    // + the producer warp
 #ifndef B200WM_EMBED_STAGES
 #define B200WM_EMBED_STAGES 3
 #endif
@@ -174,13 +173,13 @@ __device__ __forceinline__ long long item_offset(const Item& it, const StripGeom
 
 // full[s]: armed by the producer with the byte count of a load into slot s, completed by the copy engine.
 // done[s]: one arrival per consumer warp when it has finished with slot s.
-template <int kStages>
+template <int kStages, int kCW>
 __device__ __forceinline__ void init_ring(unsigned full0, unsigned done0) {
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(done0 + 8 * s, kConsumerWarps);
+            mbar_init(done0 + 8 * s, kCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -251,10 +250,15 @@ struct TilePair {
 // raw_bits must be zero on entry (the launcher clears it): warps OR their bits in.
 // kPitch: the shared-memory row pitch when it is known at compile time (1920 for 1080p strips and 4K chunks,
 // 960 for the chroma planes of 1080p yuv420p), 0 otherwise: row offsets then fold into the LDS / STS immediates.
-template <bool kWhole, bool kNarrow, unsigned kPitch>
-__global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src,
-                                                                                               ExtractArgs ex, StripGeom sg) {
+// kCW: consumer warps per CTA.  4 (two tiles per thread cover strips of up to 256 tiles, or two tile rows of up to 128)
+// for every width but strips of 170..192 tiles, whose half-strips of 85..96 tiles would leave a quarter of four warps
+// idle: those run with 3 consumer warps and one more CTA per SM (0.91-0.94 of peak against 0.87 for the vectorised-load
+// kernels, scripts/midwidth_probe.py).
+template <bool kWhole, bool kNarrow, unsigned kPitch, int kCW>
+__global__ void __launch_bounds__((kCW + 1) * 32, kCW == 3 ? B200WM_EXTRACT_MIN_CTAS + 1 : B200WM_EXTRACT_MIN_CTAS)
+dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src, ExtractArgs ex, StripGeom sg) {
     constexpr int kStages = kExtractStages;
+    constexpr int kConsumerWarps = kCW;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long bars[2 * kStages];
     __shared__ int cta_counts[kStages][32];          // per-strip vote counts, one buffer per ring slot
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TileGeom& g = sg.g;
     if (threadIdx.x < kStages * 32) cta_counts[threadIdx.x >> 5][threadIdx.x & 31] = 0;
-    init_ring<kStages>(full0, done0);
+    init_ring<kStages, kCW>(full0, done0);
     const int step = (int)gridDim.x;
     const int L = ex.payload_len;
     int stage = 0;
@@ -351,10 +355,11 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EXTRACT_MIN_CTAS) dwtsvd_e
 }
 
 // ---- embed ----------------------------------------------------------------------------------------------
-template <bool kWhole, bool kNarrow, unsigned kPitch>
-__global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                                      EmbedArgs em, StripGeom sg) {
+template <bool kWhole, bool kNarrow, unsigned kPitch, int kCW>
+__global__ void __launch_bounds__((kCW + 1) * 32, kCW == 3 ? B200WM_EMBED_MIN_CTAS + 1 : B200WM_EMBED_MIN_CTAS)
+dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EmbedArgs em, StripGeom sg) {
     constexpr int kStages = kEmbedStages;
+    constexpr int kConsumerWarps = kCW;
     static_assert(kStages >= 3, "a slot is refilled one iteration after its store was committed");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long bars[2 * kStages];
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(kCtaThreads, B200WM_EMBED_MIN_CTAS) dwtsvd_emb
     const unsigned full0 = smem_u32(&bars[0]), done0 = smem_u32(&bars[kStages]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TileGeom& g = sg.g;
-    init_ring<kStages>(full0, done0);
+    init_ring<kStages, kCW>(full0, done0);
     const int step = (int)gridDim.x;
     int stage = 0;
     unsigned parity = 0;
@@ -471,10 +476,12 @@ bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const Ti
           (pl->frame_stride_bytes % 16) == 0 && g.tiles_x >= 64 && g.tiles_y > 0))
         return false;
     if (pl->n_frames > 1 && pl->frame_stride_bytes < pl->pitch_bytes * (long long)pl->height) return false;
-    // Strips of 129..183 tiles (720p: 160, portrait 1080p: 135) carry too few bytes per work item for four CTAs
-    // of four consumer warps to keep the SM busy: measured 0.59-0.77 of peak against 0.79 for the vectorised-load
-    // kernels (scripts/midwidth_probe.py), so those planes stay on that path until the CTA shape is specialised.
-    if (g.tiles_x > kStripThreads && g.tiles_x < 184) return false;
+    // Strips of 129..169 tiles (720p: 160, portrait 1080p: 135) and of 193..215 tiles carry too few tiles per consumer
+    // thread whatever the CTA shape (measured, embed + extract, fraction of the HBM peak: 720p 0.86 with three consumer
+    // warps and one tile row per item, 0.88 with five and two rows, against 0.90 for the vectorised-load kernels;
+    // 135 tiles 0.71 / 0.74 against 0.86; 208 tiles 0.83 against 0.86 - scripts/midwidth_probe.py), so those planes
+    // stay on the vectorised-load kernels.
+    if ((g.tiles_x > kStripThreads && g.tiles_x < 170) || (g.tiles_x > 192 && g.tiles_x < 216)) return false;
     const bool whole = g.tiles_x <= kMaxStripTiles && pl->pitch_bytes == 8ll * g.tiles_x;
     if (!whole && ((pl->pitch_bytes % 16) != 0 || (g.tiles_x % 2) != 0)) return false;
     int chunk_tiles = 0;
@@ -483,19 +490,41 @@ bool tma_eligible(const void* a, const void* b, const b200wm_plane* pl, const Ti
     return items < (1ll << 26) && items * frame_items < (1ll << 40);     // exact magic divisions
 }
 
+// Grid of a persistent kernel: SMs x resident CTAs.  Asked from the runtime once per (kernel, device, shared-memory
+// size) and remembered.  (All instantiations of one kernel template share a function-pointer TYPE, hence this
+// function and its tables: entries are keyed by the kernel's address.)
 template <typename Kernel>
-static int persistent_grid(Kernel kernel, size_t smem, int* blocks) {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        B200WM_CUDA_TRY(cudaGetDevice(&dev));
-        B200WM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+static int persistent_grid(Kernel kernel, int cta_threads, size_t smem, int* blocks) {
+    struct Entry { const void* fn; int dev; size_t smem; int blocks; };
+    constexpr int kMax = 64;
+    static std::mutex mu;
+    static Entry cache[kMax];        // smem == ~0: "dynamic shared-memory limit raised for (fn, dev)"
+    static int used = 0;
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    int dev = 0;
+    B200WM_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    bool opted_in = false;
+    for (int i = 0; i < used; ++i) {
+        if (cache[i].fn != fn || cache[i].dev != dev) continue;
+        if (cache[i].smem == smem) { *blocks = cache[i].blocks; return B200WM_OK; }
+        if (cache[i].smem == ~(size_t)0) opted_in = true;
     }
-    B200WM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    B200WM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kCtaThreads, smem));
+    if (!opted_in) {
+        // once per kernel and device: allow everything the SM offers, so that launches with another strip size need no call
+        int optin = 0;
+        cudaFuncAttributes fa;
+        B200WM_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        B200WM_CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+        B200WM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+        if (used < kMax) cache[used++] = Entry{fn, dev, ~(size_t)0, 0};
+    }
+    int sms = 0, per_sm = 0;
+    B200WM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B200WM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, cta_threads, smem));
     if (per_sm < 1) per_sm = 1;
     *blocks = sms * per_sm;
+    if (used < kMax) cache[used++] = Entry{fn, dev, smem, *blocks};
     return B200WM_OK;
 }
 
@@ -516,26 +545,28 @@ static StripGeom make_strip_geom(const TileGeom& g, const b200wm_plane* pl) {
     return sg;
 }
 
-template <bool kWhole, bool kNarrow, unsigned kPitch>
+static bool mid_width(const StripGeom& sg) { return !sg.narrow && sg.chunks_x == 1 && sg.g.tiles_x <= 192; }
+
+template <bool kWhole, bool kNarrow, unsigned kPitch, int kCW = 4>
 static int launch_extract_t(const uint8_t* src, const ExtractArgs& xa, const StripGeom& sg, cudaStream_t stream) {
     const size_t smem = (size_t)kExtractStages * sg.slot_bytes;
     int blocks = 0;
-    const int rc = persistent_grid(dwtsvd_extract_tma_kernel<kWhole, kNarrow, kPitch>, smem, &blocks);
+    const int rc = persistent_grid(dwtsvd_extract_tma_kernel<kWhole, kNarrow, kPitch, kCW>, (kCW + 1) * 32, smem, &blocks);
     if (rc) return rc;
     if (sg.total < blocks) blocks = sg.total;
-    dwtsvd_extract_tma_kernel<kWhole, kNarrow, kPitch><<<blocks, kCtaThreads, smem, stream>>>(src, xa, sg);
+    dwtsvd_extract_tma_kernel<kWhole, kNarrow, kPitch, kCW><<<blocks, (kCW + 1) * 32, smem, stream>>>(src, xa, sg);
     B200WM_LAUNCH_CHECK("dwtsvd_extract_tma_kernel");
     return B200WM_OK;
 }
 
-template <bool kWhole, bool kNarrow, unsigned kPitch>
+template <bool kWhole, bool kNarrow, unsigned kPitch, int kCW = 4>
 static int launch_embed_t(const uint8_t* src, uint8_t* dst, const EmbedArgs& ea, const StripGeom& sg, cudaStream_t stream) {
     const size_t smem = (size_t)kEmbedStages * sg.slot_bytes;
     int blocks = 0;
-    const int rc = persistent_grid(dwtsvd_embed_tma_kernel<kWhole, kNarrow, kPitch>, smem, &blocks);
+    const int rc = persistent_grid(dwtsvd_embed_tma_kernel<kWhole, kNarrow, kPitch, kCW>, (kCW + 1) * 32, smem, &blocks);
     if (rc) return rc;
     if (sg.total < blocks) blocks = sg.total;
-    dwtsvd_embed_tma_kernel<kWhole, kNarrow, kPitch><<<blocks, kCtaThreads, smem, stream>>>(src, dst, ea, sg);
+    dwtsvd_embed_tma_kernel<kWhole, kNarrow, kPitch, kCW><<<blocks, (kCW + 1) * 32, smem, stream>>>(src, dst, ea, sg);
     B200WM_LAUNCH_CHECK("dwtsvd_embed_tma_kernel");
     return B200WM_OK;
 }
@@ -547,6 +578,7 @@ int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const Til
         if (sg.whole) return sg.slot_pitch == 960 ? launch_extract_t<true, true, 960>(p, xa, sg, stream) : launch_extract_t<true, true, 0>(p, xa, sg, stream);
         return launch_extract_t<false, true, 0>(p, xa, sg, stream);
     }
+    if (mid_width(sg)) return sg.whole ? launch_extract_t<true, false, 0, 3>(p, xa, sg, stream) : launch_extract_t<false, false, 0, 3>(p, xa, sg, stream);
     if (sg.whole) return sg.slot_pitch == 1920 ? launch_extract_t<true, false, 1920>(p, xa, sg, stream) : launch_extract_t<true, false, 0>(p, xa, sg, stream);
     return sg.slot_pitch == 1920 ? launch_extract_t<false, false, 1920>(p, xa, sg, stream) : launch_extract_t<false, false, 0>(p, xa, sg, stream);
 }
@@ -560,6 +592,7 @@ int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, 
         if (sg.whole) return sg.slot_pitch == 960 ? launch_embed_t<true, true, 960>(p, d, ea, sg, stream) : launch_embed_t<true, true, 0>(p, d, ea, sg, stream);
         return launch_embed_t<false, true, 0>(p, d, ea, sg, stream);
     }
+    if (mid_width(sg)) return sg.whole ? launch_embed_t<true, false, 0, 3>(p, d, ea, sg, stream) : launch_embed_t<false, false, 0, 3>(p, d, ea, sg, stream);
     if (sg.whole) return sg.slot_pitch == 1920 ? launch_embed_t<true, false, 1920>(p, d, ea, sg, stream) : launch_embed_t<true, false, 0>(p, d, ea, sg, stream);
     return sg.slot_pitch == 1920 ? launch_embed_t<false, false, 1920>(p, d, ea, sg, stream) : launch_embed_t<false, false, 0>(p, d, ea, sg, stream);
 }

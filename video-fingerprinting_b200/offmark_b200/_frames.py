@@ -37,6 +37,18 @@ class FrameOnDevice:
         return self.src
 
 
+_POOL = None
+
+
+def _copy_pool():
+    global _POOL
+    if _POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) // 2)), thread_name_prefix="b200wm-stage")
+    return _POOL
+
+
 class Staging:
     """Pinned host buffers for the batched drivers: frames are gathered into ``up`` (one H2D copy per batch at
     full link speed instead of one pageable copy per frame) and results land in ``down``.  Grown on demand,
@@ -57,8 +69,12 @@ class Staging:
         self.up = self._fit(self.up, shape)
         host = self.up[:int(np.prod(shape))].view(shape)
         view = host.numpy()
-        for i, f in enumerate(frames):
-            np.copyto(view[i], f, casting="unsafe")
+        if len(frames) >= 4 and frames[0].nbytes >= (1 << 20):
+            # numpy copies release the GIL: a few threads move the batch at several times one core's memcpy rate
+            list(_copy_pool().map(lambda i: np.copyto(view[i], frames[i], casting="unsafe"), range(len(frames))))
+        else:
+            for i, f in enumerate(frames):
+                np.copyto(view[i], f, casting="unsafe")
         return host.to(device, non_blocking=True)
 
     def download(self, tensor):
