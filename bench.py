@@ -437,8 +437,21 @@ class Batch:
         self.pos_counts = torch.empty((n_frames, PAYLOAD_LEN), dtype=torch.int32, device=dev)
         self.deg = DeShuffler(key=KEY).set_shape((PAYLOAD_LEN,))
         # two persistent vote states: the asynchronous exchange of step i overlaps step i+1, which fills the other one
-        self.votes = [SegmentVote(self.n_seg_local * world, PAYLOAD_LEN, dev, owned=(rank * self.n_seg_local, self.n_seg_local))
-                      for _ in range(2)]
+        owned = (rank * self.n_seg_local, self.n_seg_local)
+        self.exchange = "none (one GPU)"
+        self.votes = None
+        if world > 1 and os.environ.get("B200WM_EXCHANGE", "nvlink") == "nvlink":
+            try:        # peer-mapped state: the histogram kernel stores its finished block into every peer's buffer itself
+                self.votes = [SegmentVote(self.n_seg_local * world, PAYLOAD_LEN, dev, owned=owned, symmetric=True) for _ in range(2)]
+                self.exchange = "fused into the histogram kernel: 128-bit stores of the rank's block into every peer's buffer over NVLink, flag per rank (b200wm_pattern_hist_publish)"
+            except Exception as exc:        # no peer mapping on this box: the NCCL path below
+                self.votes = None
+                self.exchange_note = f"symmetric memory unavailable ({type(exc).__name__}: {str(exc)[:120]})"
+        if self.votes is None:
+            self.votes = [SegmentVote(self.n_seg_local * world, PAYLOAD_LEN, dev, owned=owned) for _ in range(2)]
+            if world > 1:
+                self.exchange = ("one asynchronous NCCL all-gather of the vote state per step, overlapped with the next step's embed; "
+                                 "the last one completes inside the timed region")
         self.step_no = 0
         self.patterns = None
 
@@ -575,9 +588,7 @@ def main():
         "kernels": {"embed_ms": k_embed, "embed_GBs": embed_gbs, "extract_ms": k_extract, "extract_GBs": extract_gbs,
                     "vote_ms": k_vote, "step_GBs": step_gbs, "step_frac_of_peak": step_gbs / peak,
                     "unaccounted_ms_per_step": ms_per_step - k_embed - k_extract - k_vote,
-                    "combine": ("none (one GPU)" if world == 1 else
-                                "one asynchronous all-gather of the 104 KB vote state per step, overlapped with the next step's "
-                                "embed; the last one completes inside the timed region"),
+                    "combine": batch.exchange, "combine_note": getattr(batch, "exchange_note", None),
                     "roofline_fps_per_gpu": peak * 1e9 / (3.0 * W * H)},
         "bit_accuracy": {"note": "against the EMBEDDED ground truth; agreement with the reference is in `parity`",
                          "segments_exact": seg_ok / batch.n_seg_local, "frames_exact": frame_ok, "raw_bits_first_64_frames": raw_acc},

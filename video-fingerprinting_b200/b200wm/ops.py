@@ -319,6 +319,19 @@ def pattern_hist(packed, payload_len, n_segments=1, frame_segment=None, frame_or
     return state
 
 
+def pattern_hist_publish(packed, payload_len, n_segments, state, frame_segment, frame_order, order_offset, peers_dev, block_len,
+                         world, rank, epoch, ticket, status):
+    """``pattern_hist`` into ``state`` (views of this rank's block) fused with the NVLink exchange of the block
+    (``b200wm_pattern_hist_publish``).  ``peers_dev``: device address of the array of peer base pointers."""
+    require_cuda()
+    check(lib.b200wm_pattern_hist_publish(_ptr(packed), _ptr(frame_segment), _ptr(frame_order), int(order_offset), packed.numel(),
+                                          int(payload_len), int(n_segments), _ptr(state["hist"]), _ptr(state["first_seen"]),
+                                          _ptr(state["bit_votes"]), _ptr(state["seg_frames"]), C.c_void_p(int(peers_dev)),
+                                          int(block_len), int(world), int(rank), int(epoch) & 0xFFFFFFFF, _ptr(ticket), _ptr(status),
+                                          _stream()))
+    return state
+
+
 def vote_state_reset(flat, n_zero):
     """``flat`` int32 CUDA tensor: entries [0, n_zero) <- 0, the rest <- INT32_MAX, one launch."""
     require_cuda()

@@ -33,7 +33,7 @@ class SegmentVote:
     nothing to reduce afterwards.  Without ``owned`` a segment may be split across ranks and ``combine``
     all-gathers the full state and reduces it locally (SUM of counters, MIN of first-seen indices)."""
 
-    def __init__(self, n_segments, payload_len, device, owned=None):
+    def __init__(self, n_segments, payload_len, device, owned=None, symmetric=False, group=None):
         if payload_len > MAX_HIST_BITS:
             raise ValueError(f"pattern histogram supports payload_len <= {MAX_HIST_BITS}; "
                              "use gathered_pattern_vote for longer payloads")
@@ -52,11 +52,34 @@ class SegmentVote:
         a, b = per * bins, per * (bins + self.payload_len)
         c = b + per
         self._block_len = c + per * bins
-        self._flat = torch.zeros(blocks * self._block_len, dtype=torch.int32, device=dev)
         self._n_sum = c
         self._work = None
         self._gathered = None
-        blk = self._flat.view(blocks, self._block_len)
+        self._symm = None
+        if symmetric:
+            # ``symmetric=True`` (owned mode, inside a process group): the state lives in peer-mapped memory and ``add``
+            # runs the histogram kernel FUSED with the NVLink exchange of this rank's block (b200wm_pattern_hist_publish):
+            # no collective call at all, ``combine`` has nothing left to do.  Collective constructor (rendezvous).
+            if not self.owned or not (dist.is_available() and dist.is_initialized()):
+                raise ValueError("symmetric=True needs owned=(first, count) and an initialised process group")
+            import torch.distributed._symmetric_memory as symm_mem
+            self._pad_len = (self._block_len + 3) // 4 * 4                 # 16-byte blocks for the 128-bit peer stores
+            world = dist.get_world_size(group)
+            if blocks != world:
+                raise ValueError("owned blocks must follow the rank order of the group")
+            buf = symm_mem.empty(world * self._pad_len + max(4, (world + 3) // 4 * 4), dtype=torch.int32, device=dev)
+            buf.zero_()
+            handle = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            self._symm = {"buf": buf, "handle": handle, "peers": int(handle.buffer_ptrs_dev), "world": world,
+                          "rank": dist.get_rank(group), "epoch": 0,
+                          "ticket": torch.zeros(1, dtype=torch.int32, device=dev), "status": torch.zeros(1, dtype=torch.int32, device=dev)}
+            torch.cuda.synchronize(dev)
+            dist.barrier(group)                                            # every peer's flags are zero before anyone publishes
+            self._flat = buf[:world * self._pad_len]
+            blk = self._flat.view(world, self._pad_len)[:, :self._block_len]
+        else:
+            self._flat = torch.zeros(blocks * self._block_len, dtype=torch.int32, device=dev)
+            blk = self._flat.view(blocks, self._block_len)
         self.hist = blk[:, :a].view(blocks, per, bins)
         self.bit_votes = blk[:, a:b].view(blocks, per, self.payload_len)
         self.seg_frames = blk[:, b:c].view(blocks, per)
@@ -70,7 +93,10 @@ class SegmentVote:
         """Back to "nothing seen" so that ONE state object serves batch after batch: a single kernel launch on the
         GPU (``b200wm_vote_state_reset``), no allocation.  Waits for a pending asynchronous ``combine`` first."""
         self.wait()
-        if self._flat.is_cuda:
+        if self._symm is not None:
+            k = self.owned[0] // self.owned[1]
+            ops.vote_state_reset(self._flat[k * self._pad_len:k * self._pad_len + self._block_len], self._n_sum)
+        elif self._flat.is_cuda:
             if self.owned:          # per block [counters | first_seen]: reset block by block views of the same run
                 blocks = self.n_segments // self.owned[1]
                 if blocks == 1:
@@ -106,6 +132,12 @@ class SegmentVote:
         n_seg = self.owned[1] if self.owned else self.n_segments
         if first and frame_segment is not None:
             frame_segment = frame_segment - first
+        if self._symm is not None:
+            s = self._symm
+            s["epoch"] += 1
+            ops.pattern_hist_publish(packed, self.payload_len, n_seg, state, frame_segment, frame_order, order_offset, s["peers"],
+                                     self._pad_len, s["world"], s["rank"], s["epoch"], s["ticket"], s["status"])
+            return self
         ops.pattern_hist(packed, self.payload_len, n_seg, frame_segment, frame_order, order_offset, state=state)
         return self
 
@@ -118,6 +150,8 @@ class SegmentVote:
         at once WITHOUT making the current stream wait for it, so that the next batch's embed overlaps the
         exchange; ``wait()`` (called by ``result`` and ``reset``) joins it."""
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return self
+        if self._symm is not None:          # exchanged by the kernel that accumulated it
             return self
         self.wait()
         world = dist.get_world_size(group)
@@ -153,6 +187,8 @@ class SegmentVote:
     def result(self):
         """Per segment: (pattern uint8 [L] or None, frequency or None, bit_votes int [L], frames)."""
         self.wait()
+        if self._symm is not None and int(self._symm["status"].item()):
+            raise RuntimeError("vote exchange timed out: a peer did not publish its block within two seconds")
         bins = 1 << self.payload_len
         hist = self.hist.cpu().numpy().reshape(self.n_segments, bins)
         first = self.first_seen.cpu().numpy().reshape(self.n_segments, bins)

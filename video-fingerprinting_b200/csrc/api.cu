@@ -22,6 +22,8 @@ int launch_vote_finish(const int32_t*, int, int, long long, const int32_t*, uint
 int launch_pattern_hist(const uint64_t*, const int32_t*, const int32_t*, int, int, int, int, int32_t*, int32_t*, int32_t*,
                         int32_t*, cudaStream_t);
 int launch_vote_state_reset(int32_t*, long long, long long, cudaStream_t);
+int launch_pattern_hist_publish(const uint64_t*, const int32_t*, const int32_t*, int, int, int, int, int32_t*, int32_t*, int32_t*,
+                                int32_t*, void* const*, long long, int, int, unsigned, unsigned*, int*, cudaStream_t);
 int launch_dct8_masks(const void*, const b200wm_plane*, float*, float*, double*, cudaStream_t);
 int launch_dct8_embed(const void*, void*, const b200wm_plane*, const float*, const float*, const double*, const uint32_t*,
                       int, int, long long, const int32_t*, float, cudaStream_t);
@@ -165,6 +167,16 @@ B200WM_API int b200wm_pattern_hist(const uint64_t* packed, const int32_t* frame_
                         int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames, void* stream) {
     return launch_pattern_hist(packed, frame_segment, frame_order, order_offset, n_frames, payload_len, n_segments, hist,
                                first_seen, bit_votes, seg_frames, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_pattern_hist_publish(const uint64_t* packed, const int32_t* frame_segment, const int32_t* frame_order,
+                               int32_t order_offset, int32_t n_frames, int32_t payload_len, int32_t n_segments, int32_t* hist,
+                               int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames, void* const* peer_states,
+                               int64_t block_len, int32_t world, int32_t rank, uint32_t epoch, uint32_t* ticket, int32_t* status,
+                               void* stream) {
+    return launch_pattern_hist_publish(packed, frame_segment, frame_order, order_offset, n_frames, payload_len, n_segments, hist,
+                                       first_seen, bit_votes, seg_frames, peer_states, block_len, world, rank, epoch, ticket, status,
+                                       (cudaStream_t)stream);
 }
 
 B200WM_API int b200wm_vote_state_reset(int32_t* state, int64_t n_zero, int64_t n_total, void* stream) {

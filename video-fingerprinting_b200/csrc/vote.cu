@@ -148,6 +148,104 @@ __global__ void __launch_bounds__(256) pattern_hist_kernel(const unsigned long l
         if ((p >> (L - 1 - j)) & 1ull) atomicAdd(&bit_votes[(long long)seg * L + j], 1);
 }
 
+// ---- pattern histogram fused with its exchange over NVLink --------------------------------------------------
+// Multi-GPU form of the cross-frame vote when whole segments are dealt to ranks (BASELINE config 4): every rank
+// keeps the per-segment state of ALL ranks in one buffer, rank-major, [world][block_len] int32 followed by `world`
+// arrival flags, allocated as symmetric memory so that every rank holds a mapped pointer to every peer's copy
+// (torch.distributed._symmetric_memory: plumbing).  ONE kernel accumulates this rank's frames into its own block
+// (the histogram atomics of pattern_hist_kernel) and, in the CTA that finishes last, stores the finished block
+// straight into the same slot of every peer's buffer with 128-bit stores over NVLink / NVSwitch, raises this
+// rank's arrival flag on every peer (release, system scope) and waits until every peer's flag shows the same
+// epoch (acquire): when the kernel ends, the local buffer holds every rank's block - what the NCCL all-gather
+// delivered before, without a second launch, a collective call or a rendezvous on the host.
+// The wait gives up after two seconds (a peer that never launches must not hang the GPU) and reports it in *status.
+struct ExchangeArgs {
+    int32_t* const* peers;     // device array [world]: base of every rank's state buffer (index `rank` = the local one)
+    long long block_len;       // int32 entries per rank block, a multiple of 4
+    int world, rank;
+    unsigned epoch;            // increases by one per exchange
+    unsigned* ticket;          // local scratch, zero before the first launch
+    int* status;               // local: set to 1 when the wait timed out
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) pattern_hist_publish_kernel(const unsigned long long* __restrict__ packed,
+                                                                   const int32_t* __restrict__ frame_segment,
+                                                                   const int32_t* __restrict__ frame_order, int order_offset,
+                                                                   int n_frames, int L, int n_segments, int32_t* hist,
+                                                                   int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames,
+                                                                   ExchangeArgs ex) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n_frames) {
+        const int seg = frame_segment ? frame_segment[f] : 0;
+        if (seg >= 0 && seg < n_segments) {
+            const unsigned long long p = packed[f];
+            const long long bin = (long long)seg * (1ll << L) + (long long)p;
+            atomicAdd(&hist[bin], 1);
+            atomicMin(&first_seen[bin], frame_order ? frame_order[f] : order_offset + f);
+            atomicAdd(&seg_frames[seg], 1);
+            for (int j = 0; j < L; ++j)
+                if ((p >> (L - 1 - j)) & 1ull) atomicAdd(&bit_votes[(long long)seg * L + j], 1);
+        }
+    }
+    // the CTA that takes the last ticket sees every other CTA's atomics (fence, then the ticket itself)
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ex.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();                                             // acquire side of the ticket
+    if (threadIdx.x == 0) *ex.ticket = 0u;                       // armed for the next launch
+    const int4* mine = reinterpret_cast<const int4*>(ex.peers[ex.rank] + (long long)ex.rank * ex.block_len);
+    const int n16 = (int)(ex.block_len / 4);
+    for (int p = 1; p < ex.world; ++p) {
+        const int peer = (ex.rank + p) % ex.world;               // every rank starts on another peer
+        int4* theirs = reinterpret_cast<int4*>(ex.peers[peer] + (long long)ex.rank * ex.block_len);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) theirs[i] = __ldcg(mine + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    const long long flags = (long long)ex.world * ex.block_len;
+    if ((int)threadIdx.x < ex.world && (int)threadIdx.x != ex.rank) {
+        unsigned* there = reinterpret_cast<unsigned*>(ex.peers[threadIdx.x] + flags) + ex.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(there), "r"(ex.epoch) : "memory");
+        const unsigned* here = reinterpret_cast<const unsigned*>(ex.peers[ex.rank] + flags) + threadIdx.x;
+        const unsigned long long t0 = global_ns();
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(here) : "memory");
+            if ((int)(seen - ex.epoch) >= 0) break;
+            if (global_ns() - t0 > 2000000000ull) { *ex.status = 1; break; }
+        } while (true);
+    }
+}
+
+int launch_pattern_hist_publish(const uint64_t* packed, const int32_t* frame_segment, const int32_t* frame_order,
+                                int order_offset, int n_frames, int payload_len, int n_segments, int32_t* hist,
+                                int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames, void* const* peers,
+                                long long block_len, int world, int rank, unsigned epoch, unsigned* ticket, int* status,
+                                cudaStream_t stream) {
+    if (!packed || !hist || !first_seen || !bit_votes || !seg_frames || n_frames < 0 || n_segments <= 0 || payload_len <= 0)
+        return B200WM_ERR_INVALID;
+    if (!peers || !ticket || !status || world < 1 || world > 256 || rank < 0 || rank >= world || block_len <= 0 || block_len % 4)
+        return B200WM_ERR_INVALID;
+    if (payload_len > 16) return B200WM_ERR_UNSUPPORTED;
+    const int threads = 256;
+    const int blocks = n_frames > 0 ? (n_frames + threads - 1) / threads : 1;      // an empty shard still takes part in the exchange
+    ExchangeArgs ex{reinterpret_cast<int32_t* const*>(peers), block_len, world, rank, epoch, ticket, status};
+    pattern_hist_publish_kernel<<<blocks, threads, 0, stream>>>((const unsigned long long*)packed, frame_segment, frame_order,
+                                                                order_offset, n_frames, payload_len, n_segments, hist, first_seen,
+                                                                bit_votes, seg_frames, ex);
+    B200WM_LAUNCH_CHECK("pattern_hist_publish_kernel");
+    return B200WM_OK;
+}
+
 // One launch that puts a vote state back to "nothing seen": zeros for the counters, INT32_MAX for first_seen.
 __global__ void __launch_bounds__(256) vote_state_reset_kernel(int32_t* __restrict__ state, long long n_zero, long long n_total) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x)
