@@ -231,16 +231,20 @@ B200WM_API int b200wm_pattern_hist(const uint64_t* packed, const int32_t* frame_
  * start) in peer-mapped ("symmetric") memory; `peer_states` is a DEVICE array of the `world` base pointers of these
  * buffers as mapped in this process (entry `rank` = the local buffer).  hist / first_seen / bit_votes / seg_frames point
  * into this rank's own block, exactly as for b200wm_pattern_hist.  The kernel accumulates the frames, then its last CTA
- * stores the block into slot `rank` of every peer's buffer (128-bit stores), raises flag[rank] = epoch on every peer and
- * waits until every local flag shows `epoch` (epochs increase by one per call, same value on every rank): on return of the
- * stream to this point the local buffer holds every rank's block.  ticket: one zeroed uint32 of local scratch; status: one
- * int32, set to 1 if a peer did not arrive within two seconds (the kernel never hangs).  block_len must be a multiple of 4.
+ * stores the block into slot `rank` of every peer's buffer (128-bit stores) and raises flag[rank] = epoch on every peer
+ * (epochs increase by one per call, same value on every rank).  One-sided: the call never waits for a peer.
+ * b200wm_vote_exchange_wait enqueues the wait - until every local flag shows `epoch` - for whoever reads the peers' blocks;
+ * status: one int32, set to 1 if a peer did not arrive within two seconds (the wait never hangs the GPU).
+ * ticket: one zeroed uint32 of local scratch.  block_len must be a multiple of 4.
  */
 B200WM_API int b200wm_pattern_hist_publish(const uint64_t* packed, const int32_t* frame_segment, const int32_t* frame_order,
                                int32_t order_offset, int32_t n_frames, int32_t payload_len, int32_t n_segments, int32_t* hist,
                                int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames, void* const* peer_states,
                                int64_t block_len, int32_t world, int32_t rank, uint32_t epoch, uint32_t* ticket, int32_t* status,
                                void* stream);
+
+B200WM_API int b200wm_vote_exchange_wait(void* const* peer_states, int64_t block_len, int32_t world, int32_t rank, uint32_t epoch,
+                             int32_t* status, void* stream);
 
 /*
  * Reset of a vote state that lives in ONE int32 run [counters (hist | bit_votes | seg_frames) | first_seen]: the

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "b200wm_pattern_hist": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "b200wm_pattern_hist_publish": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
                                               C.c_uint32, _vp, _vp, _vp]),
+    "b200wm_vote_exchange_wait": (C.c_int, [_vp, _i64, _i32, _i32, C.c_uint32, _vp, _vp]),
     "b200wm_vote_state_reset": (C.c_int, [_vp, _i64, _i64, _vp]),
     "b200wm_bgr8_to_yuv32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "b200wm_yuv32_to_bgr8": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -332,6 +332,13 @@ def pattern_hist_publish(packed, payload_len, n_segments, state, frame_segment, 
     return state
 
 
+def vote_exchange_wait(peers_dev, block_len, world, rank, epoch, status):
+    """Enqueue the wait for every peer's block of exchange ``epoch`` (``b200wm_vote_exchange_wait``)."""
+    require_cuda()
+    check(lib.b200wm_vote_exchange_wait(C.c_void_p(int(peers_dev)), int(block_len), int(world), int(rank), int(epoch) & 0xFFFFFFFF,
+                                        _ptr(status), _stream()))
+
+
 def vote_state_reset(flat, n_zero):
     """``flat`` int32 CUDA tensor: entries [0, n_zero) <- 0, the rest <- INT32_MAX, one launch."""
     require_cuda()

@@ -92,7 +92,8 @@ class SegmentVote:
     def reset(self):
         """Back to "nothing seen" so that ONE state object serves batch after batch: a single kernel launch on the
         GPU (``b200wm_vote_state_reset``), no allocation.  Waits for a pending asynchronous ``combine`` first."""
-        self.wait()
+        if self._symm is None:
+            self.wait()                     # (symmetric mode: one-sided exchange, only this rank's own block is reset)
         if self._symm is not None:
             k = self.owned[0] // self.owned[1]
             ops.vote_state_reset(self._flat[k * self._pad_len:k * self._pad_len + self._block_len], self._n_sum)
@@ -135,6 +136,7 @@ class SegmentVote:
         if self._symm is not None:
             s = self._symm
             s["epoch"] += 1
+            s["pending"] = True
             ops.pattern_hist_publish(packed, self.payload_len, n_seg, state, frame_segment, frame_order, order_offset, s["peers"],
                                      self._pad_len, s["world"], s["rank"], s["epoch"], s["ticket"], s["status"])
             return self
@@ -177,7 +179,12 @@ class SegmentVote:
             self._flat[self._n_sum:] = self._gathered[:, self._n_sum:].amin(dim=0)
 
     def wait(self):
-        """Join a pending asynchronous ``combine`` (the current stream waits for the collective)."""
+        """Join a pending asynchronous ``combine`` (the current stream waits for the collective) or, in symmetric
+        mode, enqueue the wait for the peers' blocks of the last exchange."""
+        if self._symm is not None and self._symm.get("pending"):
+            s = self._symm
+            ops.vote_exchange_wait(s["peers"], self._pad_len, s["world"], s["rank"], s["epoch"], s["status"])
+            s["pending"] = False
         if self._work is not None:
             self._work.wait()
             self._work = None

@@ -22,6 +22,7 @@ int launch_vote_finish(const int32_t*, int, int, long long, const int32_t*, uint
 int launch_pattern_hist(const uint64_t*, const int32_t*, const int32_t*, int, int, int, int, int32_t*, int32_t*, int32_t*,
                         int32_t*, cudaStream_t);
 int launch_vote_state_reset(int32_t*, long long, long long, cudaStream_t);
+int launch_vote_exchange_wait(void* const*, long long, int, int, unsigned, int*, cudaStream_t);
 int launch_pattern_hist_publish(const uint64_t*, const int32_t*, const int32_t*, int, int, int, int, int32_t*, int32_t*, int32_t*,
                                 int32_t*, void* const*, long long, int, int, unsigned, unsigned*, int*, cudaStream_t);
 int launch_dct8_masks(const void*, const b200wm_plane*, float*, float*, double*, cudaStream_t);
@@ -177,6 +178,11 @@ B200WM_API int b200wm_pattern_hist_publish(const uint64_t* packed, const int32_t
     return launch_pattern_hist_publish(packed, frame_segment, frame_order, order_offset, n_frames, payload_len, n_segments, hist,
                                        first_seen, bit_votes, seg_frames, peer_states, block_len, world, rank, epoch, ticket, status,
                                        (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_vote_exchange_wait(void* const* peer_states, int64_t block_len, int32_t world, int32_t rank, uint32_t epoch,
+                             int32_t* status, void* stream) {
+    return launch_vote_exchange_wait(peer_states, block_len, world, rank, epoch, status, (cudaStream_t)stream);
 }
 
 B200WM_API int b200wm_vote_state_reset(int32_t* state, int64_t n_zero, int64_t n_total, void* stream) {

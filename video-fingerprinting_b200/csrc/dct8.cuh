@@ -1,6 +1,7 @@
 // Register-resident 8-point DCT-II / DCT-III butterflies (orthonormal, like cv2.dct / cv2.idct).
 #pragma once
 #include <cuda_runtime.h>
+#include "common.cuh"
 
 namespace b200wm {
 
@@ -67,5 +68,45 @@ __device__ __forceinline__ void idct8x8(float (&b)[64]) {
     for (int y = 0; y < 8; ++y)
         idct8_1d(b[8 * y], b[8 * y + 1], b[8 * y + 2], b[8 * y + 3], b[8 * y + 4], b[8 * y + 5], b[8 * y + 6], b[8 * y + 7]);
 }
+
+// Fast path for planar uint8 with 8-byte aligned rows: eight 64-bit loads per block, and every byte
+// becomes a float by PRMT into the mantissa of 1.5 * 2^23 (value 12582912 + byte, exact) - no
+// byte loads, no I2F.  Differences of two such values are the exact sample differences, and an FMA
+// that adds a small increment to one rounds sample + increment to the nearest integer (ties to even)
+// and leaves it in the low mantissa bits, ready for the 16-bit saturating pack below.
+constexpr unsigned kBiasBits = 0x4B400000u;
+constexpr float kBias = 12582912.0f;
+
+__device__ __forceinline__ void load_rows_u8(const uint8_t* p, long long pitch, uint2 (&rows)[8]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) rows[y] = ldg_stream_u2(p + y * pitch);
+}
+template <int kByte>
+__device__ __forceinline__ float mid_biased_byte(unsigned w) {      // 32768 + byte: [0x47][0x00][byte][0x00]
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404 | (kByte << 4)));
+}
+template <int kByte>
+__device__ __forceinline__ float biased_byte(unsigned w) {
+    return __uint_as_float(__byte_perm(w, kBiasBits, 0x7640 | kByte));
+}
+// b[8*y + x] = kBias + sample
+__device__ __forceinline__ void biased_block(const uint2 (&rows)[8], float (&b)[64]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        b[8 * y + 0] = biased_byte<0>(rows[y].x); b[8 * y + 1] = biased_byte<1>(rows[y].x);
+        b[8 * y + 2] = biased_byte<2>(rows[y].x); b[8 * y + 3] = biased_byte<3>(rows[y].x);
+        b[8 * y + 4] = biased_byte<0>(rows[y].y); b[8 * y + 5] = biased_byte<1>(rows[y].y);
+        b[8 * y + 6] = biased_byte<2>(rows[y].y); b[8 * y + 7] = biased_byte<3>(rows[y].y);
+    }
+}
+// eight floats holding kBias + integer -> eight bytes clamped to [0, 255]
+__device__ __forceinline__ uint2 pack_biased_row(const float (&f)[8]) {
+    unsigned lanes[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        lanes[k] = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(f[2 * k]), __float_as_uint(f[2 * k + 1]), 0x5410), 0u, 0x00FF00FFu);
+    return make_uint2(__byte_perm(lanes[0], lanes[1], 0x6420), __byte_perm(lanes[2], lanes[3], 0x6420));
+}
+
 
 }  // namespace b200wm
