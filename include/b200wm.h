@@ -235,7 +235,7 @@ B200WM_API int b200wm_pattern_hist(const uint64_t* packed, const int32_t* frame_
  * (epochs increase by one per call, same value on every rank).  One-sided: the call never waits for a peer.
  * b200wm_vote_exchange_wait enqueues the wait - until every local flag shows `epoch` - for whoever reads the peers' blocks;
  * status: one int32, set to 1 if a peer did not arrive within two seconds (the wait never hangs the GPU).
- * ticket: one zeroed uint32 of local scratch.  block_len must be a multiple of 4.
+ * ticket: two zeroed uint32 of local scratch.  At most 128 - 4 (world - 1) histogram CTAs (256 frames each) per call.  block_len must be a multiple of 4.
  */
 B200WM_API int b200wm_pattern_hist_publish(const uint64_t* packed, const int32_t* frame_segment, const int32_t* frame_order,
                                int32_t order_offset, int32_t n_frames, int32_t payload_len, int32_t n_segments, int32_t* hist,

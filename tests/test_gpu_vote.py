@@ -115,3 +115,36 @@ def test_owned_block_layout_equals_general_layout():
             assert np.array_equal(a[0], b[0])
     with pytest.raises(ValueError):
         SegmentVote(10, L, DEV, owned=(3, 5))
+
+
+def test_pattern_hist_publish_equals_pattern_hist_on_one_gpu():
+    """b200wm_pattern_hist_publish (histogram fused with the NVLink exchange of the finished block) with a world of one
+    rank: same state as b200wm_pattern_hist, counters re-armed, and the wait kernel returns at once.  The multi-GPU
+    exchange itself is checked against the NCCL all-gather by scripts/publish_check.py under torchrun (2 and 8 GPUs)."""
+    from b200wm import ops
+    dev = torch.device("cuda:0")
+    L, n_seg = 8, 7
+    gen = torch.Generator(device=dev).manual_seed(3)
+    for n in (0, 1, 300, 5000):
+        packed = torch.randint(0, 1 << L, (n,), device=dev, generator=gen, dtype=torch.int64)
+        seg = torch.randint(0, n_seg, (n,), device=dev, generator=gen, dtype=torch.int32)
+        want = ops.pattern_hist(packed, L, n_seg, seg, None, 11) if n else None
+        bins = 1 << L
+        block_len = (n_seg * (2 * bins + L + 1) + 3) // 4 * 4
+        buf = torch.zeros(block_len + 4, dtype=torch.int32, device=dev)
+        a, b, c = n_seg * bins, n_seg * (bins + L), n_seg * (bins + L + 1)
+        state = {"hist": buf[:a].view(n_seg, bins), "bit_votes": buf[a:b].view(n_seg, L), "seg_frames": buf[b:c],
+                 "first_seen": buf[c:c + n_seg * bins].view(n_seg, bins)}
+        state["first_seen"].fill_(ops.INT32_MAX)
+        peers = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=dev)
+        ticket, status = torch.zeros(2, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+        for epoch in (1, 2):                     # twice: the counters must have been re-armed by the first launch
+            ops.pattern_hist_publish(packed, L, n_seg, state, seg, None, 11, peers.data_ptr(), block_len, 1, 0, epoch, ticket, status)
+            ops.vote_exchange_wait(peers.data_ptr(), block_len, 1, 0, epoch, status)
+        torch.cuda.synchronize()
+        assert ticket.tolist() == [0, 0] and status.item() == 0
+        if n:
+            assert torch.equal(state["hist"], 2 * want["hist"]) and torch.equal(state["first_seen"], want["first_seen"])
+            assert torch.equal(state["bit_votes"], 2 * want["bit_votes"]) and torch.equal(state["seg_frames"], 2 * want["seg_frames"])
+        else:
+            assert not state["hist"].any()

@@ -72,7 +72,7 @@ class SegmentVote:
             handle = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
             self._symm = {"buf": buf, "handle": handle, "peers": int(handle.buffer_ptrs_dev), "world": world,
                           "rank": dist.get_rank(group), "epoch": 0,
-                          "ticket": torch.zeros(1, dtype=torch.int32, device=dev), "status": torch.zeros(1, dtype=torch.int32, device=dev)}
+                          "ticket": torch.zeros(2, dtype=torch.int32, device=dev), "status": torch.zeros(1, dtype=torch.int32, device=dev)}
             torch.cuda.synchronize(dev)
             dist.barrier(group)                                            # every peer's flags are zero before anyone publishes
             self._flat = buf[:world * self._pad_len]
@@ -135,6 +135,18 @@ class SegmentVote:
             frame_segment = frame_segment - first
         if self._symm is not None:
             s = self._symm
+            # the fused kernel takes at most 128 - 4 (world - 1) CTAs of 256 frames (its helper CTAs spin, so the whole grid
+            # must be resident): longer batches accumulate their head with the plain histogram kernel
+            limit = (128 - 4 * (s["world"] - 1)) * 256
+            n = packed.numel()
+            if n > limit:
+                head = n - limit
+                ops.pattern_hist(packed[:head], self.payload_len, n_seg, None if frame_segment is None else frame_segment[:head].contiguous(),
+                                 None if frame_order is None else frame_order[:head].contiguous(), order_offset, state=state)
+                packed = packed[head:]
+                frame_segment = None if frame_segment is None else frame_segment[head:].contiguous()
+                frame_order = None if frame_order is None else frame_order[head:].contiguous()
+                order_offset += head
             s["epoch"] += 1
             s["pending"] = True
             ops.pattern_hist_publish(packed, self.payload_len, n_seg, state, frame_segment, frame_order, order_offset, s["peers"],

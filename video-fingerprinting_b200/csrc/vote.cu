@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(256) pattern_hist_kernel(const unsigned long l
 // keeps the per-segment state of ALL ranks in one buffer, rank-major, [world][block_len] int32 followed by `world`
 // arrival flags, allocated as symmetric memory so that every rank holds a mapped pointer to every peer's copy
 // (torch.distributed._symmetric_memory: plumbing).  ONE kernel accumulates this rank's frames into its own block
-// (the histogram atomics of pattern_hist_kernel) and, in the CTA that finishes last, stores the finished block
-// straight into the same slot of every peer's buffer with 128-bit stores over NVLink / NVSwitch, raises this
-// rank's arrival flag on every peer (release, system scope) - what the NCCL all-gather delivered before, without a
+// (the histogram atomics of pattern_hist_kernel) and, in helper CTAs of the same launch that wait for the histogram
+// CTAs' tickets, stores the finished block straight into the same slot of every peer's buffer with 128-bit stores over
+// NVLink / NVSwitch (four CTAs per peer) and raises this rank's arrival flag on every peer (release, system scope) - what the NCCL all-gather delivered before, without a
 // second launch, a collective call or a rendezvous on the host.  The exchange is ONE-SIDED: nothing in the step waits
 // for a peer, so a rank that runs a little slower does not hold the others back every step (with the wait inside the
 // kernel the 8-GPU step measured 0.14 ms of vote time, all of it skew between the ranks).  Whoever needs the peers'
@@ -167,7 +167,7 @@ struct ExchangeArgs {
     long long block_len;       // int32 entries per rank block, a multiple of 4
     int world, rank;
     unsigned epoch;            // increases by one per exchange
-    unsigned* ticket;          // local scratch, zero before the first launch
+    unsigned* ticket;          // local scratch, two counters, zero before the first launch
     int* status;               // local: set to 1 when the wait timed out
 };
 
@@ -177,12 +177,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-__global__ void __launch_bounds__(256) pattern_hist_publish_kernel(const unsigned long long* __restrict__ packed,
-                                                                   const int32_t* __restrict__ frame_segment,
-                                                                   const int32_t* __restrict__ frame_order, int order_offset,
-                                                                   int n_frames, int L, int n_segments, int32_t* hist,
-                                                                   int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames,
-                                                                   ExchangeArgs ex) {
+__device__ __forceinline__ void hist_and_ticket(const unsigned long long* __restrict__ packed, const int32_t* __restrict__ frame_segment,
+                                                const int32_t* __restrict__ frame_order, int order_offset, int n_frames, int L,
+                                                int n_segments, int32_t* hist, int32_t* first_seen, int32_t* bit_votes,
+                                                int32_t* seg_frames, const ExchangeArgs& ex) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < n_frames) {
         const int seg = frame_segment ? frame_segment[f] : 0;
@@ -196,28 +194,73 @@ __global__ void __launch_bounds__(256) pattern_hist_publish_kernel(const unsigne
                 if ((p >> (L - 1 - j)) & 1ull) atomicAdd(&bit_votes[(long long)seg * L + j], 1);
         }
     }
-    // the CTA that takes the last ticket sees every other CTA's atomics (fence, then the ticket itself)
-    __shared__ bool is_last;
+    // every histogram CTA takes a ticket behind a fence: whoever reads ticket == n_hist (acquire) sees all their atomics
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(ex.ticket, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) atomicAdd(&ex.ticket[0], 1u);
+}
+
+// Helper CTAs of the same launch (blockIdx >= n_hist; kPublishSplit per peer): wait until every histogram CTA has
+// taken its ticket, then store one slice of the finished block into one peer's buffer; the helper that finishes last
+// raises this rank's flag on every peer and re-arms the counters.  All CTAs of the launch are co-resident (a few dozen
+// on 148 SMs), so the wait cannot starve the CTAs it waits for; it still gives up after two seconds.
+constexpr int kPublishSplit = 4;
+
+__device__ __forceinline__ void publish_slice(const ExchangeArgs& ex, int n_hist, int helper) {
+    __shared__ bool go;
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = global_ns();
+        unsigned seen;
+        go = true;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ex.ticket) : "memory");
+            if (seen >= (unsigned)n_hist) break;
+            if (global_ns() - t0 > 2000000000ull) { *ex.status = 1; go = false; break; }
+            __nanosleep(200);
+        } while (true);
+    }
     __syncthreads();
-    if (!is_last) return;
-    __threadfence();                                             // acquire side of the ticket
-    if (threadIdx.x == 0) *ex.ticket = 0u;                       // armed for the next launch
-    const int4* mine = reinterpret_cast<const int4*>(ex.peers[ex.rank] + (long long)ex.rank * ex.block_len);
-    const int n16 = (int)(ex.block_len / 4);
-    for (int p = 1; p < ex.world; ++p) {
-        const int peer = (ex.rank + p) % ex.world;               // every rank starts on another peer
+    const int peer_slot = helper / kPublishSplit, part = helper % kPublishSplit;
+    const int peer = (ex.rank + 1 + peer_slot) % ex.world;              // every rank starts on another peer
+    if (go) {
+        const int4* mine = reinterpret_cast<const int4*>(ex.peers[ex.rank] + (long long)ex.rank * ex.block_len);
         int4* theirs = reinterpret_cast<int4*>(ex.peers[peer] + (long long)ex.rank * ex.block_len);
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) theirs[i] = __ldcg(mine + i);
+        const int n16 = (int)(ex.block_len / 4), per = (n16 + kPublishSplit - 1) / kPublishSplit;
+        const int hi = min(n16, (part + 1) * per);
+        for (int i = part * per + threadIdx.x; i < hi; i += blockDim.x) theirs[i] = __ldcg(mine + i);
     }
     __threadfence_system();
     __syncthreads();
-    const long long flags = (long long)ex.world * ex.block_len;
-    if ((int)threadIdx.x < ex.world && (int)threadIdx.x != ex.rank) {
+    __shared__ bool is_last;
+    const int n_helpers = (ex.world - 1) * kPublishSplit;
+    if (threadIdx.x == 0) is_last = atomicAdd(&ex.ticket[1], 1u) == (unsigned)(n_helpers - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence_system();
+    if (go && (int)threadIdx.x < ex.world && (int)threadIdx.x != ex.rank) {
+        const long long flags = (long long)ex.world * ex.block_len;
         unsigned* there = reinterpret_cast<unsigned*>(ex.peers[threadIdx.x] + flags) + ex.rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(there), "r"(ex.epoch) : "memory");
+    }
+    if (threadIdx.x == 0) { ex.ticket[0] = 0u; ex.ticket[1] = 0u; }      // armed for the next launch
+}
+
+__global__ void __launch_bounds__(256) pattern_hist_publish_kernel(const unsigned long long* __restrict__ packed,
+                                                                   const int32_t* __restrict__ frame_segment,
+                                                                   const int32_t* __restrict__ frame_order, int order_offset,
+                                                                   int n_frames, int L, int n_segments, int32_t* hist,
+                                                                   int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames,
+                                                                   ExchangeArgs ex, int n_hist) {
+    if ((int)blockIdx.x >= n_hist) {
+        publish_slice(ex, n_hist, (int)blockIdx.x - n_hist);
+        return;
+    }
+    hist_and_ticket(packed, frame_segment, frame_order, order_offset, n_frames, L, n_segments, hist, first_seen, bit_votes, seg_frames, ex);
+    if (ex.world == 1 && threadIdx.x == 0 && blockIdx.x == 0) {
+        // no helpers to re-arm the ticket: the first CTA waits for the others' tickets (all resident) and clears it
+        unsigned seen;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ex.ticket) : "memory"); } while (seen < (unsigned)n_hist);
+        ex.ticket[0] = 0u;
     }
 }
 
@@ -249,17 +292,18 @@ int launch_pattern_hist_publish(const uint64_t* packed, const int32_t* frame_seg
                                 int32_t* first_seen, int32_t* bit_votes, int32_t* seg_frames, void* const* peers,
                                 long long block_len, int world, int rank, unsigned epoch, unsigned* ticket, int* status,
                                 cudaStream_t stream) {
-    if (!packed || !hist || !first_seen || !bit_votes || !seg_frames || n_frames < 0 || n_segments <= 0 || payload_len <= 0)
+    if ((!packed && n_frames > 0) || !hist || !first_seen || !bit_votes || !seg_frames || n_frames < 0 || n_segments <= 0 || payload_len <= 0)
         return B200WM_ERR_INVALID;
     if (!peers || !ticket || !status || world < 1 || world > 256 || rank < 0 || rank >= world || block_len <= 0 || block_len % 4)
         return B200WM_ERR_INVALID;
     if (payload_len > 16) return B200WM_ERR_UNSUPPORTED;
     const int threads = 256;
-    const int blocks = n_frames > 0 ? (n_frames + threads - 1) / threads : 1;      // an empty shard still takes part in the exchange
+    const int n_hist = n_frames > 0 ? (n_frames + threads - 1) / threads : 1;      // an empty shard still takes part in the exchange
+    if (n_hist + (world - 1) * kPublishSplit > 128) return B200WM_ERR_UNSUPPORTED;  // helpers spin: every CTA must be resident at once
     ExchangeArgs ex{reinterpret_cast<int32_t* const*>(peers), block_len, world, rank, epoch, ticket, status};
-    pattern_hist_publish_kernel<<<blocks, threads, 0, stream>>>((const unsigned long long*)packed, frame_segment, frame_order,
-                                                                order_offset, n_frames, payload_len, n_segments, hist, first_seen,
-                                                                bit_votes, seg_frames, ex);
+    pattern_hist_publish_kernel<<<n_hist + (world - 1) * kPublishSplit, threads, 0, stream>>>(
+        (const unsigned long long*)packed, frame_segment, frame_order, order_offset, n_frames, payload_len, n_segments, hist, first_seen,
+        bit_votes, seg_frames, ex, n_hist);
     B200WM_LAUNCH_CHECK("pattern_hist_publish_kernel");
     return B200WM_OK;
 }
