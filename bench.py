@@ -57,11 +57,12 @@ PAYLOAD = np.array([0, 1, 1, 0, 0, 1, 0, 1])
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--steps", type=int, default=30)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--frames", type=int, default=3000, help="frames per GPU")
     p.add_argument("--e2e-frames", type=int, default=3000)
+    p.add_argument("--e2e-chunk", type=int, default=0, help="frames per chunk inside the host-buffer calls (0: the library's 64 MB default)")
     p.add_argument("--plugin-frames", type=int, default=256)
     p.add_argument("--attack-frames", type=int, default=10000)
     p.add_argument("--attack-oracle-frames", type=int, default=64)
@@ -717,7 +718,7 @@ def _run_e2e(args, ops, batch, dev, world):
 
     def mark_verify():
         return ops.dwtsvd_mark_verify_host(host_in, host_marked, rows_host, perm, scale=15.0, frame_wm_row=frame_row_host,
-                                           wm_len=batch.wm_len)
+                                           wm_len=batch.wm_len, chunk_frames=args.e2e_chunk)
 
     def mark_then_detect():
         ops.dwtsvd_mark_host(host_in, host_marked, rows_host, scale=15.0, frame_wm_row=frame_row_host, wm_len=batch.wm_len)

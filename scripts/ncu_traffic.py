@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""profiles/r01_traffic.json from a full-size `ncu --set full` capture of the two hot kernels.
+"""profiles/r02_traffic.json from a full-size `ncu --set full` capture of the two hot kernels.
 
 On the GPU box (after the same command has exited 0 without ncu):
     ncu --set full --clock-control none --import-source on -k regex:dwtsvd -s 2 -c 2 -o gpurun_out/prof_full3000 \
         python bench.py --steps 2 --warmup 1 --frames 3000 --no-e2e --no-cpu-baseline
 Here:
-    python scripts/ncu_traffic.py gpurun_out/prof_full3000.ncu-rep 3000 > profiles/r01_traffic.json
+    python scripts/ncu_traffic.py gpurun_out/prof_full3000.ncu-rep 3000 > profiles/r02_traffic.json
 """
 import csv
 import json
@@ -37,4 +37,4 @@ for r in rows[2:]:
         "block": int(val("launch__block_size")),
     }
 print(json.dumps({"source": f"ncu --set full --clock-control none, python bench.py --steps 2 --warmup 1 --frames {frames} "
-                            "--no-e2e --no-cpu-baseline, round 1 (scripts/ncu_traffic.py)", "kernels": kernels}, indent=1))
+                            "--no-e2e --no-cpu-baseline, round 2 (scripts/ncu_traffic.py)", "kernels": kernels}, indent=1))
