@@ -4,7 +4,7 @@
 All frames are generated, marked, attacked and read back on the GPU (b200wm kernels); on a
 subsample per attack the reference extractor (oracle restatement, CPU) reads the very same attacked
 frames so that the two bit-error rates can be put side by side.  Prints a markdown table.
-    python tests/studies/attack_study.py [--frames 10000] [--oracle-frames 32]
+    python tests/studies/attack_study.py [--frames 10000] [--oracle-frames 64]
 
 Lives under tests/ because it runs the oracle (as the checker) next to the CUDA path: only tests/, smoke() and
 bench.py's CPU legs may do that.
@@ -47,7 +47,7 @@ def make_frames(n, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=10000)
-    ap.add_argument("--oracle-frames", type=int, default=32)
+    ap.add_argument("--oracle-frames", type=int, default=64)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     n, block_num = args.frames, H * W // 64
