@@ -912,7 +912,9 @@ def leg_dct8(ops, batch, dev, peak, pool, n=512):
     return {"metric": "frames_per_sec_1080p_dct8_embed_extract", "value": n / (step_ms * 1e-3), "unit": "frames/s", "frames": n,
             "layout": "planar uint8 4:4:4 (masks from Y, mark in U)",
             "roofline": {"bound": "hbm", "kernel": "dct8_masks_kernel", "achieved": w * h * n / (ms_m * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": w * h * n / (ms_m * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": w * h * n},
+                         "frac": w * h * n / (ms_m * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": w * h * n,
+                         "note": "this kernel is FP32-pipe bound, not HBM bound: 640 FP32 operations per 64-byte block (full 2-D DCT "
+                                 "butterflies + magnitude sums) put its ceiling at 0.57 of the HBM peak at 100 % FP32 issue (DESIGN.md 4.4)"},
             "kernels": {"masks_ms": ms_m, "masks_frac": w * h * n / (ms_m * 1e-3) / 1e9 / peak,
                         "embed_ms": ms_e, "embed_frac": 2 * w * h * n / (ms_e * 1e-3) / 1e9 / peak,
                         "extract_ms": ms_x, "extract_frac": w * h * n / (ms_x * 1e-3) / 1e9 / peak,

@@ -167,6 +167,63 @@ def main():
     fx["vote_pattern"], fx["vote_frequency"] = best, np.float64(freq)
     np.savez_compressed(os.path.join(OUT, "in_mp4_frames.npz"), **fx)
 
+    # ---------------------------------------------------------------- the reference's two media fixtures, whole
+    # The two files are small (0.4 MB + 0.3 MB) test DATA of the reference, copied next to the goldens so that the GPU
+    # box - which has no /root/reference - can run the very inputs the reference's own scripts use at full size:
+    # frame63.jpeg at 1080p and all 209 frames of in.mp4.  What the reference made of them is stored as hashes, packed
+    # bits and patterns; the oracle reproduces the marked frames on the box and the hashes prove it is still the
+    # reference's output there.
+    import shutil
+    media = os.path.join(OUT, "media")
+    os.makedirs(media, exist_ok=True)
+    meta["media"] = {}
+    for rel in (("imgs", "frame63.jpeg"), ("in.mp4",)):
+        src_path = os.path.join(REF, "tests", "media", *rel)
+        shutil.copyfile(src_path, os.path.join(media, rel[-1]))
+        with open(src_path, "rb") as fh:
+            meta["media"][rel[-1]] = {"from": "tests/media/" + "/".join(rel), "sha256": hashlib.sha256(fh.read()).hexdigest()}
+    print("frame63.jpeg, whole 1080p frame, both coder pairs")
+    fx = {"bgr_sha256": np.array(sha(img))}
+    for tag, enc_cls, dec_cls, o_e, o_d in (("dwtsvd", DwtDctSvdEncoder, DwtDctSvdDecoder, o_svd.encode, o_svd.decode),
+                                            ("dct8", DctEncoder, DctDecoder, o_dct.encode, o_dct.decode)):
+        enc, dec = enc_cls(), dec_cls()
+        wm = Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(img.shape))
+        enc.read_wm(wm)
+        deg = DeShuffler(key=KEY).set_shape(PAYLOAD.shape)
+        yuv0 = cv2.cvtColor(img.astype(np.float32), cv2.COLOR_BGR2YUV)
+        yuv_ref = enc.encode(yuv0.copy())
+        same(o_e(yuv0.copy(), wm), yuv_ref, f"frame63 full {tag} encode")
+        marked = ref_mark_frame(img, enc)
+        fx[f"{tag}_marked_f32_ch1_sha256"] = np.array(sha(yuv_ref[:, :, 1]))
+        fx[f"{tag}_marked_u8_sha256"] = np.array(sha(marked))
+        for name, src in (("clean", yuv0), ("marked_f32", yuv_ref),
+                          ("marked_u8", cv2.cvtColor(marked.astype(np.float32), cv2.COLOR_BGR2YUV))):
+            bits = dec.decode(src.copy())
+            same(o_d(src.copy()), bits, f"frame63 full {tag} decode {name}")
+            fx[f"{tag}_bits_{name}"] = np.packbits(bits.astype(np.uint8).reshape(-1))
+            fx[f"{tag}_pattern_{name}"] = deg.degenerate(bits)
+        fx[f"{tag}_nbits"] = np.int64(bits.size)
+    np.savez_compressed(os.path.join(OUT, "frame63_full.npz"), **fx)
+
+    print("in.mp4, all 209 frames through mark.py + detect.py (in memory)")
+    enc, dec = DwtDctSvdEncoder(), DwtDctSvdDecoder()
+    wm = Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(frames[0].shape))
+    enc.read_wm(wm)
+    deg = DeShuffler(key=KEY).set_shape(PAYLOAD.shape)
+    src_sha, marked_sha, bits_all, pats = [], [], [], []
+    for i, f in enumerate(frames):
+        marked = ref_mark_frame(f, enc)
+        bits, pat = ref_check_frame(marked, dec, deg)
+        src_sha.append(sha(f))
+        marked_sha.append(sha(marked))
+        bits_all.append(np.packbits(bits.astype(np.uint8).reshape(-1)))
+        pats.append(pat)
+        if i % 19 == 0:
+            same(o_br.mark_frame(f, lambda y: o_svd.encode(y, wm)), marked, f"in.mp4[{i}] mark_frame (all-frames pass)")
+    assert np.array_equal(np.array(pats), patterns)
+    np.savez_compressed(os.path.join(OUT, "in_mp4_all.npz"), src_sha256=np.array(src_sha), marked_sha256=np.array(marked_sha),
+                        bits_marked=np.stack(bits_all), patterns=np.array(pats), nbits=np.int64(bits.size))
+
     # ---------------------------------------------------------------- synthetic float yuv, odd sizes
     print("seeded synthetic float32 frames, sizes that exercise the truncation rules")
     fx = {}

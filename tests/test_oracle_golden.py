@@ -197,3 +197,64 @@ def test_flat_blocks_are_exact_in_the_reference_restatement():
     # the case that motivated it: flat 255 reads as bit 1 (sigma_0 = 2039.99988, not 2040 = 136 * 15)
     assert o_svd.extract_plane(np.full((8, 8), 255, dtype=np.uint8))[0, 0] == 1.0
     assert o_svd.extract_plane(np.full((8, 8), 30, dtype=np.uint8))[0, 0] == 0.0
+
+
+# ---- the reference's two media fixtures at full size (tests/golden/media, copied by oracle/make_golden.py) ----------
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def load_frame63(golden_dir):
+    import cv2
+    img = cv2.imread(os.path.join(golden_dir, "media", "frame63.jpeg"))
+    g = np.load(os.path.join(golden_dir, "frame63_full.npz"))
+    if img is None or _sha(img) != str(g["bgr_sha256"]):
+        pytest.skip("this OpenCV build decodes frame63.jpeg differently from the one the goldens were made with")
+    return img, g
+
+
+def load_in_mp4(golden_dir):
+    import cv2
+    cap = cv2.VideoCapture(os.path.join(golden_dir, "media", "in.mp4"))
+    frames = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(np.ascontiguousarray(f[:, :, ::-1]))     # BGR -> rgb24 byte order, like FileDecoder (frame_reader.py:59-63)
+    cap.release()
+    g = np.load(os.path.join(golden_dir, "in_mp4_all.npz"))
+    if len(frames) != len(g["src_sha256"]) or any(_sha(f) != str(s) for f, s in zip(frames, g["src_sha256"])):
+        pytest.skip("this OpenCV / FFmpeg build decodes in.mp4 differently from the one the goldens were made with")
+    return frames, g
+
+
+def test_oracle_equals_reference_on_whole_frame63(golden_dir):
+    """frame63.jpeg at its full 1080p through both coder pairs: the oracle's marked frames hash to what the REFERENCE
+    produced (oracle/make_golden.py ran it), its decoders return the reference's bits."""
+    img, g = load_frame63(golden_dir)
+    for tag, mod in (("dwtsvd", svd), ("dct8", dct8)):
+        wm = payload.generate_wm(PAYLOAD, (1, img.shape[0] * img.shape[1] // 64), 0)
+        yuv = mod.encode(bracket.to_yuv(img), wm)
+        assert _sha(yuv[:, :, 1]) == str(g[f"{tag}_marked_f32_ch1_sha256"])
+        marked = bracket.from_yuv(yuv.copy())
+        assert _sha(marked) == str(g[f"{tag}_marked_u8_sha256"])
+        n = int(g[f"{tag}_nbits"])
+        for name, src in (("clean", bracket.to_yuv(img)), ("marked_f32", yuv), ("marked_u8", bracket.to_yuv(marked))):
+            assert np.array_equal(mod.decode(src.copy())[0].astype(np.uint8), _bits(g[f"{tag}_bits_{name}"], n)[0]), (tag, name)
+        assert np.array_equal(g[f"{tag}_pattern_marked_u8"], PAYLOAD)
+
+
+def test_oracle_equals_reference_on_all_209_frames_of_in_mp4(golden_dir):
+    """tests/mark.py + tests/detect.py on the reference's clip, every frame: marked frames hash to the reference's,
+    raw bits and per-frame patterns are the reference's."""
+    frames, g = load_in_mp4(golden_dir)
+    wm = payload.generate_wm(PAYLOAD, (1, 240 * 320 // 64), 0)
+    n = int(g["nbits"])
+    for i, f in enumerate(frames):
+        marked = bracket.mark_frame(f, lambda y: svd.encode(y, wm))
+        assert _sha(marked) == str(g["marked_sha256"][i]), i
+        bits = svd.decode(bracket.to_yuv(marked))
+        assert np.array_equal(bits[0].astype(np.uint8), np.unpackbits(g["bits_marked"][i])[:n]), i
+        assert np.array_equal(payload.degenerate(bits, 8, 0), g["patterns"][i]), i
