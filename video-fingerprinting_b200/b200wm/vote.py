@@ -60,6 +60,9 @@ class SegmentVote:
             # ``symmetric=True`` (owned mode, inside a process group): the state lives in peer-mapped memory and ``add``
             # runs the histogram kernel FUSED with the NVLink exchange of this rank's block (b200wm_pattern_hist_publish):
             # no collective call at all, ``combine`` has nothing left to do.  Collective constructor (rendezvous).
+            # The exchange is one-sided: a peer's next ``add`` to the SAME state object overwrites its slot in this rank's
+            # buffer, so a state must have been read (``result()``) on every rank before any rank re-uses it - use two
+            # state objects alternately (as bench.py does) when batches are pipelined.
             if not self.owned or not (dist.is_available() and dist.is_initialized()):
                 raise ValueError("symmetric=True needs owned=(first, count) and an initialised process group")
             import torch.distributed._symmetric_memory as symm_mem
