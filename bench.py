@@ -19,7 +19,8 @@ Besides the headline the line carries legs that are measured OUTSIDE the headlin
     parity               8 frames of the batch against the oracle (embed LSB distance, raw-bit agreement, votes)
     e2e                  the same metric through b200wm_dwtsvd_mark_verify_host on pinned HOST planes
     e2e_mark_then_detect ... through b200wm_dwtsvd_mark_host + b200wm_dwtsvd_detect_host (round-1 e2e: 3 trips)
-    e2e_plugin_rgb24     ... through the plugin objects Embedder / Extractor on rgb24 host frames
+    e2e_plugin_rgb24     ... through the plugin objects Embedder / Extractor on rgb24 host frames (per-frame read / write;
+                         e2e_plugin_rgb24_batch_io: the same objects with the optional batch reader / writer protocol)
     config3_4k           BASELINE configs[2]: 4K planes, 256 frames per GPU, with its own roofline (every N)
     pair_dct8            the 8x8-DCT plugin pair (DctEncoder / DctDecoder) on 4:4:4 planar uint8 (N = 1)
     attacks              BASELINE configs[4]: BER after JPEG-like / noise / resize on 10,000 frames, against the
@@ -761,10 +762,11 @@ def _run_e2e(args, ops, batch, dev, world):
     del host_in, host_marked
     if h == 1080:
         out["e2e_plugin_rgb24"] = plugin_leg(args, ops, batch, dev, world)
+        out["e2e_plugin_rgb24_batch_io"] = plugin_leg(args, ops, batch, dev, world, pinned_io=True)
     return out
 
 
-def plugin_leg(args, ops, batch, dev, world):
+def plugin_leg(args, ops, batch, dev, world, pinned_io=False):
     """The reference's own driver flow on its own data format: rgb24 host frames -> Embedder.start() -> marked rgb24
     host frames -> Extractor.start() -> per-frame patterns (video/embedder.py:17-39, video/extractor.py:17-34), with
     the drop-in classes in batched mode.  Python-level frame handling is inside the timed region."""
@@ -774,44 +776,54 @@ def plugin_leg(args, ops, batch, dev, world):
     from offmark_b200.degenerator.de_shuffler import DeShuffler
     from offmark_b200.video.embedder import Embedder
     from offmark_b200.video.extractor import Extractor
-    from offmark_b200.video.memory_io import ArrayReader
+    from offmark_b200.video.memory_io import ArrayReader, BatchReader, BatchWriter
 
     n, h, w = min(args.plugin_frames, batch.n), batch.h, batch.w
     # rgb24 frames whose luma is the batch's Y plane and whose chroma is mildly coloured (so U is not a flat 0.5)
     y = batch.src[:n].float()
     cb = y_planes(batch.i420, h, w)[:n].roll(31, dims=2).float() * 0.25 + 96.0
     rgb = torch.stack([(y * 0.8 + cb * 0.2 + 10).clamp(0, 255), y, (y * 0.7 + 60 - cb * 0.1).clamp(0, 255)], dim=3).round().to(torch.uint8)
-    frames = list(rgb.cpu().numpy())
+    clip = rgb.cpu().pin_memory().numpy() if pinned_io else rgb.cpu().numpy()
     del rgb, y, cb
 
     class Sink:                                          # consumes a frame inside write(), like the ffmpeg pipe
         def __init__(self):
-            self.out = np.empty((n, h, w, 3), dtype=np.uint8)
+            self.array = np.empty((n, h, w, 3), dtype=np.uint8)
             self.k = 0
 
         def write(self, f):
-            self.out[self.k] = f
+            self.array[self.k] = f
             self.k += 1
 
         def close(self):
             pass
-    state = {}
 
     def flow():
         enc = DwtDctSvdEncoder()
         enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity((h, w, 3))))
-        sink = Sink()
-        Embedder(ArrayReader(frames), enc, sink, batch_frames=32).start()
-        ex = Extractor(ArrayReader(list(sink.out)), DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((PAYLOAD_LEN,)), batch_frames=32)
+        if pinned_io:       # the optional batch protocol: batches move from / into the reader's and writer's pinned memory
+            sink = BatchWriter(n, (h, w, 3)) if "sink" not in state else state["sink"]
+            sink.count = 0
+            state["sink"] = sink
+            Embedder(BatchReader(clip), enc, sink, batch_frames=32).start()
+            reader = BatchReader(sink.array)
+        else:               # the reference's read() / write() per frame on pageable arrays
+            sink = Sink()
+            Embedder(ArrayReader(list(clip)), enc, sink, batch_frames=32).start()
+            reader = ArrayReader(list(sink.array))
+        ex = Extractor(reader, DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((PAYLOAD_LEN,)), batch_frames=32)
         ex.start()
-        state["patterns"], state["marked"] = ex.patterns, sink.out
         return ex.patterns
-    fps, dt, patterns = _wall_fps(flow, n, world, dev, 2)
+    state = {}
+    fps, _, patterns = _wall_fps(flow, n, world, dev, 2)
     ok = float(np.mean([np.array_equal(p, PAYLOAD) for p in patterns]))
+    how = ("BatchReader / BatchWriter over pinned arrays (optional batch protocol: whole batches move from / into the reader's and "
+           "writer's memory)" if pinned_io else
+           "pageable rgb24 numpy frames through per-frame read() / write() (uploads staged through pinned buffers by copy threads; the "
+           "sink copies every frame, as a pipe would)")
     return {"value": fps, "unit": "frames/s", "frames_per_gpu": n, "steps": 2, "h2d_bytes_per_step": 2 * n * h * w * 3,
             "d2h_bytes_per_step": n * h * w * 3 + n * PAYLOAD_LEN, "frames_exact": ok,
-            "path": "offmark_b200 Embedder(batch_frames=32).start() + Extractor(batch_frames=32).start() on pageable rgb24 numpy "
-                    "frames (fused rgb24 kernels; uploads staged through pinned buffers; per-frame Python read()/write())"}
+            "path": "offmark_b200 Embedder(batch_frames=32).start() + Extractor(batch_frames=32).start(), fused rgb24 kernels, " + how}
 
 
 # --------------------------------------------------------------------------------- BASELINE configs[2]: 4K

@@ -360,3 +360,44 @@ def test_argument_checks_of_the_wrappers():
             assert not raw.any().item() and not counts.any().item()
         ops.set_path(0)
     torch.cuda.synchronize()
+
+
+def test_batch_reader_writer_protocol_equals_per_frame_flow():
+    """Optional batch protocol of the drivers (video/memory_io.py: BatchReader.read_batch, BatchWriter.reserve / commit):
+    frames go up and come down as whole batches from / into the reader's and writer's own (pinned) memory; the marked
+    bytes and the logged patterns equal the reference-shaped per-frame loop's, including a ragged last batch, and the
+    plain read() / write() of the same objects still work."""
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.extract.dwt_dct_svd_decoder import DwtDctSvdDecoder
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.degenerator.de_shuffler import DeShuffler
+    from offmark_b200.video.embedder import Embedder
+    from offmark_b200.video.extractor import Extractor
+    from offmark_b200.video.memory_io import ArrayReader, ArrayWriter, BatchReader, BatchWriter
+    from oracle import synth
+    frames = np.stack([synth.random_bgr(128, 192, s) for s in range(7)])
+
+    def encoder():
+        enc = DwtDctSvdEncoder()
+        enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(frames[0].shape)))
+        return enc
+    ref_writer = ArrayWriter()
+    Embedder(ArrayReader(list(frames)), encoder(), ref_writer).start()                      # per-frame loop
+    pinned = torch.from_numpy(frames).pin_memory()
+    for reader, writer in ((BatchReader(pinned.numpy()), BatchWriter(len(frames), frames[0].shape)),
+                           (BatchReader(frames), BatchWriter(len(frames), frames[0].shape, pinned=False)),
+                           (BatchReader(frames), ArrayWriter()), (ArrayReader(list(frames)), BatchWriter(len(frames), frames[0].shape))):
+        Embedder(reader, encoder(), writer, batch_frames=3).start()
+        assert len(writer.frames) == len(frames)
+        for a, b in zip(ref_writer.frames, writer.frames):
+            assert np.array_equal(a, b)
+    marked = np.stack(ref_writer.frames)
+    want = Extractor(ArrayReader(list(marked)), DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((8,)))
+    want.start()
+    got = Extractor(BatchReader(marked), DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((8,)), batch_frames=4)
+    got.start()
+    assert len(want.patterns) == len(got.patterns) == len(frames)
+    for a, b in zip(want.patterns, got.patterns):
+        assert np.array_equal(a, b) and np.array_equal(a, PAYLOAD)
+    r = BatchReader(frames)                         # the reference's own protocol on the same object
+    assert np.array_equal(r.read(), frames[0]) and np.array_equal(r.read_batch(100), frames[1:]) and r.read() is None

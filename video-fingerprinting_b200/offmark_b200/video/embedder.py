@@ -26,6 +26,16 @@ class Embedder:
     def start(self):
         logger.debug('Entering start()')
         batched = self.batch_frames > 1 and hasattr(self.frame_embedder, "mark_rgb8")
+        if batched and hasattr(self.frame_reader, "read_batch"):
+            self._run_batches()
+        else:
+            self._run_frames(batched)
+        self.frame_reader.close()
+        self.frame_writer.close()
+        logger.info('Done')
+
+    def _run_frames(self, batched):
+        """The reference's loop (embedder.py:19-27): one ``read()`` per frame; batched mode gathers ``batch_frames`` of them."""
         pending = []
         while True:
             in_frame = self.frame_reader.read()
@@ -40,9 +50,15 @@ class Embedder:
                 self._flush(pending)
         if pending:
             self._flush(pending)
-        self.frame_reader.close()
-        self.frame_writer.close()
-        logger.info('Done')
+
+    def _run_batches(self):
+        """Readers with the optional batch protocol (video/memory_io.py:BatchReader) hand over ``[n, H, W, 3]`` views."""
+        while True:
+            frames = self.frame_reader.read_batch(self.batch_frames)
+            if frames is None or len(frames) == 0:
+                logger.info('End of input stream')
+                break
+            self._flush_array(np.ascontiguousarray(frames, dtype=np.uint8))
 
     def _flush(self, pending):
         """One upload, one fused kernel launch and one download for the whole batch; frames are written
@@ -58,6 +74,22 @@ class Embedder:
             for f in marked:
                 self.frame_writer.write(f)
         pending.clear()
+
+    def _flush_array(self, frames):
+        """A batch that is already one ``[n, H, W, 3]`` array: one copy up (asynchronous and at link speed when the
+        reader's memory is pinned), one launch, one copy down - straight into the writer's memory when it offers
+        ``reserve`` / ``commit``."""
+        dev = device_of(self.device)
+        host = torch.from_numpy(frames)
+        marked = self.frame_embedder.mark_rgb8(host.to(dev, non_blocking=host.is_pinned()))
+        dest = self.frame_writer.reserve(len(frames), frames.shape[1:]) if hasattr(self.frame_writer, "reserve") else None
+        if dest is not None:
+            torch.from_numpy(dest).copy_(marked, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.frame_writer.commit(len(frames))
+            return
+        for f in self._staging.download(marked):
+            self.frame_writer.write(f)
 
     def mark_frame(self, frame_rgb):
         """uint8 H x W x 3 in, uint8 H x W x 3 out (numpy)."""

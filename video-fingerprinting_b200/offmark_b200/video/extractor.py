@@ -27,6 +27,15 @@ class Extractor:
         logger.debug('Entering start()')
         batched = (self.batch_frames > 1 and hasattr(self.frame_extractor, "decode_rgb8")
                    and hasattr(self.degenerator, "degenerate_counts"))
+        if batched and hasattr(self.frame_reader, "read_batch"):
+            self._run_batches()
+        else:
+            self._run_frames(batched)
+        self.frame_reader.close()
+        logger.info('Done')
+
+    def _run_frames(self, batched):
+        """The reference's loop (extractor.py:19-26): one ``read()`` per frame; batched mode gathers ``batch_frames`` of them."""
         pending = []
         while True:
             in_frame = self.frame_reader.read()
@@ -41,8 +50,20 @@ class Extractor:
                 self._flush(pending)
         if pending:
             self._flush(pending)
-        self.frame_reader.close()
-        logger.info('Done')
+
+    def _run_batches(self):
+        """Readers with the optional batch protocol (video/memory_io.py:BatchReader) hand over ``[n, H, W, 3]`` views."""
+        while True:
+            frames = self.frame_reader.read_batch(self.batch_frames)
+            if frames is None or len(frames) == 0:
+                logger.info('End of input stream')
+                break
+            if self.frame_extractor.scales[1] <= 0:
+                for f in frames:
+                    self._log(self.check_frame(f))
+                continue
+            host = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.uint8))
+            self._vote_batch(host.to(device_of(self.device), non_blocking=host.is_pinned()))
 
     def _log(self, pattern):
         self.patterns.append(pattern)
@@ -54,20 +75,22 @@ class Extractor:
         dev = device_of(self.device)
         same = all(f.shape == pending[0].shape for f in pending)
         for group in ([pending] if same else [[f] for f in pending]):
-            frames = self._staging.upload(group, dev)
-            h, w = frames.shape[1], frames.shape[2]
-            scale = self.frame_extractor.scales[1]
-            length = self.degenerator.payload_len
-            if scale <= 0:
+            if self.frame_extractor.scales[1] <= 0:
                 for f in group:
                     self._log(self.check_frame(f))
                 continue
-            raw, counts = ops.dwtsvd_extract_rgb8(frames, scale=scale, channel=1, payload_len=length)
-            patterns, _ = self.degenerator.degenerate_counts(counts, h * w // 64)
-            fmt = getattr(self.degenerator, "format_pattern", None)
-            for p in patterns.cpu().numpy():
-                self._log(fmt(p) if fmt else p)
+            self._vote_batch(self._staging.upload(group, dev))
         pending.clear()
+
+    def _vote_batch(self, frames):
+        """uint8 ``[n, H, W, 3]`` CUDA frames -> one fused extract launch, one vote launch, n logged patterns."""
+        h, w = frames.shape[1], frames.shape[2]
+        raw, counts = ops.dwtsvd_extract_rgb8(frames, scale=self.frame_extractor.scales[1], channel=1,
+                                              payload_len=self.degenerator.payload_len)
+        patterns, _ = self.degenerator.degenerate_counts(counts, h * w // 64)
+        fmt = getattr(self.degenerator, "format_pattern", None)
+        for p in patterns.cpu().numpy():
+            self._log(fmt(p) if fmt else p)
 
     def check_frame(self, frame_rgb):
         dev = device_of(self.device)
