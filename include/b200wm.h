@@ -188,6 +188,23 @@ B200WM_API int b200wm_dct8_extract(const void* src, const b200wm_plane* plane,
                         float alpha, uint32_t* raw_bits, int32_t words_per_frame,
                         int32_t payload_len, int32_t* pos_counts, void* stream);
 
+/*
+ * The pair as the reference calls it: DctEncoder.encode (embed/dct_encoder.py:18-39) and DctDecoder.decode
+ * (extract/dct_decoder.py:10-27) each compute BOTH masks of the luminance channel and then walk the chroma blocks.
+ * One call each, no caller-visible mask arrays: the masks kernel and the quantiser kernel back to back, the 8 bytes per
+ * block between them in stream-ordered scratch.  `lum` and `src` are the two channels of the same frames: same dtype,
+ * height, width and frame count, any pitches / strides (channel 0 and channel 1 of the reference's interleaved float32
+ * frames, or the Y and a full-resolution chroma plane of planar uint8 4:4:4).  frame_sum [n_frames] float64 is scratch
+ * that the call fills (the sum of the block means per frame).  Same results as b200wm_dct8_masks + b200wm_dct8_embed /
+ * _extract, which remain for callers that reuse the masks of one luminance plane for embed AND extract.
+ */
+B200WM_API int b200wm_dct8_encode(const void* lum, const b200wm_plane* lum_plane, const void* src, void* dst, const b200wm_plane* plane,
+                      double* frame_sum, const uint32_t* wm_packed, int32_t n_wm_rows, int32_t wm_words, int64_t wm_len,
+                      const int32_t* frame_wm_row, float alpha, void* stream);
+B200WM_API int b200wm_dct8_decode(const void* lum, const b200wm_plane* lum_plane, const void* src, const b200wm_plane* plane,
+                      double* frame_sum, float alpha, uint32_t* raw_bits, int32_t words_per_frame, int32_t payload_len,
+                      int32_t* pos_counts, void* stream);
+
 /* ---- votes ------------------------------------------------------------------------ */
 /*
  * Counting half of DeShuffler.degenerate for any payload_len (de_shuffler.py:17-18)

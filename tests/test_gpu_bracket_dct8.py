@@ -208,3 +208,50 @@ def test_dct8_uint8_planes_fast_path_vs_generic_and_oracle():
     assert np.array_equal(o_pay.degenerate(bits.astype(np.float64), 8, KEY), PAYLOAD)
     yuv[:, :, 1] = u_a
     assert np.array_equal(o_pay.degenerate(o_dct.decode(yuv), 8, KEY), PAYLOAD)
+
+
+def test_dct8_fused_calls_equal_the_three_kernel_path(golden_dir):
+    """b200wm_dct8_encode / _decode (the pair as the reference calls it: masks + quantiser per call, no caller-visible
+    mask arrays) give the very planes, raw bits and counts of b200wm_dct8_masks + _embed / _extract - on the reference's
+    float32 interleaved layout, planar uint8 (vector path) and unaligned planar uint8 (generic path), batched with
+    per-frame watermark rows - and the plugin classes, which use them, still match the oracle."""
+    from b200wm import ops
+    rng = np.random.RandomState(5)
+    frames = np.stack([synth.random_bgr(136, 200, s) for s in range(3)])
+    frames[1, :24, :32] = 200                                   # flat blocks: c21 == 0 exactly, stay unmarked
+    n_bits = 136 * 200 // 64
+    rows = rng.randint(0, 2, (2, n_bits))
+    packed, n = ops.pack_bits(rows, device=DEV)
+    frame_row = torch.tensor([0, 1, 0], dtype=torch.int32, device=DEV)
+    # float32 interleaved
+    yuv = np.stack([bracket.to_yuv(f) for f in frames])
+    a, b = torch.from_numpy(yuv.copy()).to(DEV), torch.from_numpy(yuv.copy()).to(DEV)
+    masks = ops.dct8_masks(a, channel=0)
+    ops.dct8_embed_(a, masks, packed, n, alpha=20, channel=1, frame_wm_row=frame_row)
+    ops.dct8_encode_(b, b, packed, n, alpha=20, lum_channel=0, channel=1, frame_wm_row=frame_row)
+    assert torch.equal(a, b)
+    raw_a, cnt_a = ops.dct8_extract(a, ops.dct8_masks(a, channel=0), alpha=20, payload_len=8, channel=1)
+    raw_b, cnt_b = ops.dct8_decode(b, b, alpha=20, payload_len=8, lum_channel=0, channel=1)
+    assert torch.equal(raw_a, raw_b) and torch.equal(cnt_a, cnt_b)
+    # planar uint8, aligned and unaligned
+    for aligned in (True, False):
+        def planes(c):
+            src = np.ascontiguousarray(frames[:, :, :, c])
+            if aligned:
+                return torch.from_numpy(src.copy()).to(DEV)
+            big = torch.zeros((3, 137, 211), dtype=torch.uint8, device=DEV)
+            view = big[:, 1:, 3:203]
+            view.copy_(torch.from_numpy(src))
+            return view
+        ya, ua, ub = planes(1), planes(0), planes(0)
+        masks = ops.dct8_masks(ya)
+        ops.dct8_embed_(ua, masks, packed, n, alpha=20, frame_wm_row=frame_row)
+        ops.dct8_encode_(ya, ub, packed, n, alpha=20, frame_wm_row=frame_row)
+        assert torch.equal(ua, ub), aligned
+        raw_a, cnt_a = ops.dct8_extract(ua, masks, alpha=20, payload_len=8)
+        raw_b, cnt_b = ops.dct8_decode(ya, ub, alpha=20, payload_len=8)
+        assert torch.equal(raw_a, raw_b) and torch.equal(cnt_a, cnt_b), aligned
+    with pytest.raises(ValueError):                              # the two channels must share dtype and geometry
+        ops.dct8_decode(torch.zeros((1, 64, 64), dtype=torch.uint8, device=DEV), torch.zeros((1, 64, 72), dtype=torch.uint8, device=DEV))
+    with pytest.raises(IndexError):
+        ops.dct8_encode_(ya, ub, packed[:, :1].contiguous(), 32)

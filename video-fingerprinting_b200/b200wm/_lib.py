@@ -45,6 +45,8 @@ PROTOTYPES = {
     "b200wm_dct8_masks": (C.c_int, [_vp, _PP, _vp, _vp, _vp, _vp]),
     "b200wm_dct8_embed": (C.c_int, [_vp, _vp, _PP, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _f32, _vp]),
     "b200wm_dct8_extract": (C.c_int, [_vp, _PP, _vp, _vp, _vp, _f32, _vp, _i32, _i32, _vp, _vp]),
+    "b200wm_dct8_encode": (C.c_int, [_vp, _PP, _vp, _vp, _PP, _vp, _vp, _i32, _i32, _i64, _vp, _f32, _vp]),
+    "b200wm_dct8_decode": (C.c_int, [_vp, _PP, _vp, _PP, _vp, _f32, _vp, _i32, _i32, _vp, _vp]),
     "b200wm_vote_counts": (C.c_int, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "b200wm_vote_finish": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b200wm_pattern_hist": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

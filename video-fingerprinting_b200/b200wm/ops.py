@@ -275,6 +275,33 @@ def dct8_extract(planes, masks, alpha=20.0, payload_len=None, channel=None):
     return raw_bits, pos_counts
 
 
+def dct8_encode_(lum, planes, wm_packed, wm_len, alpha=20.0, lum_channel=None, channel=None, frame_wm_row=None, validate_rows=False):
+    """``DctEncoder.encode`` in one call, no mask arrays: masks from ``lum`` (channel ``lum_channel`` of interleaved
+    frames) and the quantiser on ``planes`` (channel ``channel``), in place.  Returns ``planes``."""
+    require_cuda()
+    lv, lpl = describe(lum, lum_channel)
+    v, pl = describe(planes, channel)
+    _check_wm(wm_packed, frame_wm_row, pl.n_frames, validate_rows)
+    frame_sum = _empty((pl.n_frames,), torch.float64, v.device)
+    check(lib.b200wm_dct8_encode(_ptr(lv), C.byref(lpl), _ptr(v), _ptr(v), C.byref(pl), _ptr(frame_sum), _ptr(wm_packed),
+                                 wm_packed.shape[0], wm_packed.shape[1], int(wm_len), _ptr(frame_wm_row), float(alpha), _stream()))
+    return planes
+
+
+def dct8_decode(lum, planes, alpha=20.0, payload_len=None, lum_channel=None, channel=None):
+    """``DctDecoder.decode`` in one call -> (raw_bits int32 [N, words], pos_counts int32 [N, payload_len] or None)."""
+    require_cuda()
+    lv, lpl = describe(lum, lum_channel)
+    v, pl = describe(planes, channel)
+    _, _, words = geometry(pl.height, pl.width)
+    raw_bits = _empty((pl.n_frames, words), torch.int32, v.device)
+    pos_counts = torch.empty((pl.n_frames, payload_len), dtype=torch.int32, device=v.device) if payload_len is not None else None
+    frame_sum = _empty((pl.n_frames,), torch.float64, v.device)
+    check(lib.b200wm_dct8_decode(_ptr(lv), C.byref(lpl), _ptr(v), C.byref(pl), _ptr(frame_sum), float(alpha), _ptr(raw_bits), words,
+                                 int(payload_len or 0), _ptr(pos_counts), _stream()))
+    return raw_bits, pos_counts
+
+
 # ----------------------------------------------------------------------------- votes
 def vote_counts(raw_bits, block_num, payload_len):
     require_cuda()

@@ -14,6 +14,19 @@ void set_cuda_error(cudaError_t e, const char* where) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int retain_async_pool() {
+    static std::atomic<unsigned long long> done{0};
+    int dev = 0;
+    B200WM_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && ((done.load(std::memory_order_relaxed) >> dev) & 1ull)) return B200WM_OK;
+    cudaMemPool_t pool;
+    B200WM_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;
+    B200WM_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_relaxed);
+    return B200WM_OK;
+}
+
 int launch_dwtsvd_embed(const void*, void*, const b200wm_plane*, const uint32_t*, int, int, long long, const int32_t*, float,
                         cudaStream_t);
 int launch_dwtsvd_extract(const void*, const b200wm_plane*, float, uint32_t*, int, int, int32_t*, float*, cudaStream_t);
@@ -30,6 +43,10 @@ int launch_dct8_embed(const void*, void*, const b200wm_plane*, const float*, con
                       int, int, long long, const int32_t*, float, cudaStream_t);
 int launch_dct8_extract(const void*, const b200wm_plane*, const float*, const float*, const double*, float, uint32_t*, int,
                         int, int32_t*, cudaStream_t);
+int launch_dct8_encode(const void*, const b200wm_plane*, const void*, void*, const b200wm_plane*, double*, const uint32_t*, int, int,
+                       long long, const int32_t*, float, cudaStream_t);
+int launch_dct8_decode(const void*, const b200wm_plane*, const void*, const b200wm_plane*, double*, float, uint32_t*, int, int,
+                       int32_t*, cudaStream_t);
 int launch_bgr8_to_yuv32(const uint8_t*, float*, long long, cudaStream_t);
 int launch_attack_jpeg(const void*, void*, const b200wm_plane*, int, cudaStream_t);
 int launch_dwtsvd_embed_copies(const void*, const b200wm_plane*, void*, long long, int, const uint32_t*, int, int, long long,
@@ -151,6 +168,20 @@ B200WM_API int b200wm_dct8_extract(const void* src, const b200wm_plane* plane, c
                         int32_t payload_len, int32_t* pos_counts, void* stream) {
     return launch_dct8_extract(src, plane, block_mean, tex_mask, frame_sum, alpha, raw_bits, words_per_frame, payload_len,
                                pos_counts, (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_dct8_encode(const void* lum, const b200wm_plane* lum_plane, const void* src, void* dst, const b200wm_plane* plane,
+                      double* frame_sum, const uint32_t* wm_packed, int32_t n_wm_rows, int32_t wm_words, int64_t wm_len,
+                      const int32_t* frame_wm_row, float alpha, void* stream) {
+    return launch_dct8_encode(lum, lum_plane, src, dst, plane, frame_sum, wm_packed, n_wm_rows, wm_words, wm_len, frame_wm_row, alpha,
+                              (cudaStream_t)stream);
+}
+
+B200WM_API int b200wm_dct8_decode(const void* lum, const b200wm_plane* lum_plane, const void* src, const b200wm_plane* plane,
+                      double* frame_sum, float alpha, uint32_t* raw_bits, int32_t words_per_frame, int32_t payload_len,
+                      int32_t* pos_counts, void* stream) {
+    return launch_dct8_decode(lum, lum_plane, src, plane, frame_sum, alpha, raw_bits, words_per_frame, payload_len, pos_counts,
+                              (cudaStream_t)stream);
 }
 
 B200WM_API int b200wm_vote_counts(const uint32_t* raw_bits, int32_t n_frames, int32_t words_per_frame, int64_t block_num,

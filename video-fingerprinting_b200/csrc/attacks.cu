@@ -418,6 +418,8 @@ int launch_attack_resize(const void* src, const b200wm_plane* sp, void* dst, con
     auto with_tables = [&](int mode, size_t entry) -> int {      // mode: 0 linear, 1 area (spans), 2 + 16 tx + 64 ty area with fixed tap counts
         const int area = mode & 3, taps_x = (mode >> 4) & 3, taps_y = (mode >> 6) & 3;
         void* tab = nullptr;
+        const int rc_pool = retain_async_pool();
+        if (rc_pool) return rc_pool;
         B200WM_CUDA_TRY(cudaMallocAsync(&tab, entry * (size_t)(dp->width + dp->height), stream));
         void* tab_y = (uint8_t*)tab + entry * (size_t)dp->width;
         resize_tables_kernel<<<(dp->width + dp->height + 255) / 256, 256, 0, stream>>>(area, tab, tab_y, sp->width, sp->height, dp->width,

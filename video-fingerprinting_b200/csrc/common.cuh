@@ -29,6 +29,11 @@ void count_launch(int n = 1);
         ::b200wm::count_launch();                                          \
     } while (0)
 
+// Stream-ordered scratch (cudaMallocAsync) is used for per-call tables and mask arrays.  By default the runtime's pool
+// hands freed memory back to the driver at the next synchronisation, which makes every call pay for a fresh allocation
+// (measured: 1 ms per 130 MB); this keeps what the pool has, once per device.
+int retain_async_pool();
+
 // ---- geometry -----------------------------------------------------------------------
 struct TileGeom {
     int tiles_x;         // 8x8-sample tiles per row that the reference walks

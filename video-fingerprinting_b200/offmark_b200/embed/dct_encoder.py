@@ -5,8 +5,8 @@ from .._frames import FrameOnDevice
 
 class DctEncoder:
     """Same constructor, ``read_wm`` / ``wm_capacity`` / ``encode`` as the reference class
-    (dct_encoder.py:4-39).  Masks (:41-102) run in ``b200wm_dct8_masks`` on channel 0, the
-    block loop (:24-38) in ``b200wm_dct8_embed`` on channel 1."""
+    (dct_encoder.py:4-39).  ``b200wm_dct8_encode``: the masks of channel 0 (:41-102) and the block
+    loop on channel 1 (:24-38) in one call, no mask arrays."""
 
     def __init__(self, key=None, alpha=20, device=None):
         self.key = key
@@ -23,6 +23,5 @@ class DctEncoder:
     def encode(self, yuv):
         frame = FrameOnDevice(yuv, self.device)
         packed, n = ops.pack_bits(self.wm, device=frame.dev.device)
-        masks = ops.dct8_masks(frame.dev, channel=0)
-        ops.dct8_embed_(frame.dev, masks, packed, n, alpha=self.alpha, channel=1)
+        ops.dct8_encode_(frame.dev, frame.dev, packed, n, alpha=self.alpha, lum_channel=0, channel=1)
         return frame.write_back()

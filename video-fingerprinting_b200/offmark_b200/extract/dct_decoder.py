@@ -17,6 +17,5 @@ class DctDecoder:
         frame = FrameOnDevice(yuv, self.device)
         rows, cols, _ = frame.dev.shape
         block_num = rows * cols // 8 // 8
-        masks = ops.dct8_masks(frame.dev, channel=0)
-        raw, _ = ops.dct8_extract(frame.dev, masks, alpha=self.alpha, channel=1)
+        raw, _ = ops.dct8_decode(frame.dev, frame.dev, alpha=self.alpha, lum_channel=0, channel=1)
         return ops.unpack_bits(raw, block_num).astype(np.float64).reshape(1, -1)
