@@ -326,7 +326,12 @@ __device__ __forceinline__ unsigned extract_bits_x2(const f2 (&S)[16], float sca
     f2 sigma = mul2(bc2(0.5f), p.sigma0);
     f2 q, rem;
     floor_divmod2(sigma, scale, inv_scale, q, rem);
-    if (p.flat_x | p.flat_y) {
+#ifndef B200WM_NO_FLAT_RULE      // (tuning aid: what the rule costs)
+    if (p.flat_x | p.flat_y)
+#else
+    if (false)
+#endif
+    {
         const bool edge_x = p.flat_x && on_boundary<true>(sigma.x, rem.x, scale), edge_y = p.flat_y && on_boundary<true>(sigma.y, rem.y, scale);
         const float fx = edge_x ? probe(0) : __int_as_float(0x7FC00000), fy = edge_y ? probe(1) : __int_as_float(0x7FC00000);
         if (fx == fx) sigma.x = flat_sigma_ref(fx);
@@ -346,7 +351,12 @@ __device__ __forceinline__ void embed_deltas_x2(const f2 (&S)[16], unsigned bits
     f2 sigma = mul2(bc2(0.5f), p.sigma0);
     f2 q, rem;
     floor_divmod2(sigma, scale, inv_scale, q, rem);
-    if (p.flat_x | p.flat_y) {
+#ifndef B200WM_NO_FLAT_RULE
+    if (p.flat_x | p.flat_y)
+#else
+    if (false)
+#endif
+    {
         const bool edge_x = p.flat_x && on_boundary<false>(sigma.x, rem.x, scale), edge_y = p.flat_y && on_boundary<false>(sigma.y, rem.y, scale);
         const float fx = edge_x ? probe(0) : __int_as_float(0x7FC00000), fy = edge_y ? probe(1) : __int_as_float(0x7FC00000);
         if (fx == fx) sigma.x = flat_sigma_ref(fx);

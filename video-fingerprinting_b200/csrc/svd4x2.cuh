@@ -119,8 +119,13 @@ __device__ __forceinline__ Pair2 top_singular_x2(const f2 (&S)[16], f2 (&v)[4]) 
     w[2] = add2(add2(G[2], G[5]), add2(G[7], G[8]));
     w[3] = add2(add2(G[3], G[6]), add2(G[8], G[9]));
     symv4x2(G, w, x);
+#ifdef B200WM_FLAT_FROM_GRAM     // (tuning aid) the same filter from the first two Gram entries
+    out.flat_x = G[0].x == G[1].x;
+    out.flat_y = G[0].y == G[1].y;
+#else
     out.flat_x = x[0].x == x[1].x;
     out.flat_y = x[0].y == x[1].y;
+#endif
     symv4x2(G, x, w);
     // rayleigh_check, two lanes
     const f2 xw = dot4x2(x, w), xx = dot4x2(x, x);
