@@ -148,3 +148,39 @@ def test_pattern_hist_publish_equals_pattern_hist_on_one_gpu():
             assert torch.equal(state["bit_votes"], 2 * want["bit_votes"]) and torch.equal(state["seg_frames"], 2 * want["seg_frames"])
         else:
             assert not state["hist"].any()
+
+
+def test_symmetric_segment_vote_in_a_one_rank_group():
+    """SegmentVote(symmetric=True) - state in peer-mapped memory, histogram kernel fused with the exchange - inside a
+    process group of one rank: same results as the plain state, across reset and re-use, and for a batch longer than one
+    fused launch may take (the head then goes through the plain histogram kernel)."""
+    import socket
+    import torch.distributed as dist
+    from b200wm.vote import SegmentVote
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=dev)
+    try:
+        L, n_seg = 8, 5
+        try:
+            fused = SegmentVote(n_seg, L, dev, owned=(0, n_seg), symmetric=True)
+        except Exception as exc:                 # no peer-mappable memory on this box
+            pytest.skip(f"symmetric memory unavailable: {exc}")
+        plain = SegmentVote(n_seg, L, dev)
+        gen = torch.Generator(device=dev).manual_seed(9)
+        for n in (700, 40000, 3):                # 40000 > 128 * 256 frames: head + fused tail
+            packed = torch.randint(0, 1 << L, (n,), device=dev, generator=gen, dtype=torch.int64)
+            seg = torch.randint(0, n_seg, (n,), device=dev, generator=gen, dtype=torch.int32)
+            a = plain.reset().add(packed, frame_segment=seg, order_offset=5).combine().result()
+            b = fused.reset().add(packed, frame_segment=seg, order_offset=5).combine().result()
+            for x, y in zip(a, b):
+                assert (x[0] is None and y[0] is None) or (x[0].tolist() == y[0].tolist() and x[1] == y[1])
+                assert x[2].tolist() == y[2].tolist() and x[3] == y[3]
+            assert torch.equal(plain.first_seen.reshape(-1), fused.first_seen.reshape(-1))
+    finally:
+        dist.destroy_process_group()
