@@ -166,3 +166,27 @@ def test_gpu_resize_random_geometries():
         uh, uw = int(rng.randint(1, 140)), int(rng.randint(1, 160))
         got = ops.attack_resize(t, (uw, uh), ops.INTER_LINEAR).cpu().numpy()
         assert np.array_equal(got, cv2.resize(src, (uw, uh), interpolation=cv2.INTER_LINEAR)), ((sh, sw), (uh, uw))
+
+
+def test_jpeg_requant_vector_and_generic_paths_agree():
+    """The conversion-free 64-bit path of the JPEG-like requantiser (8-byte aligned rows) and the byte-wise generic path
+    (unaligned view) give the same planes, in place and batched; nothing outside the 8x8-covered area is written."""
+    from b200wm import ops
+    rng = np.random.RandomState(12)
+    base = rng.randint(0, 256, (3, 75, 203)).astype(np.uint8)
+    base[0, :16, :24] = 255
+    base[1, 8:24, 40:64] = 0
+    for q in (95, 60, 20):
+        a = torch.from_numpy(base.copy()).to(DEV)
+        aligned = torch.zeros((3, 75, 208), dtype=torch.uint8, device=DEV)[:, :, :203]      # pitch 208: vector path
+        aligned.copy_(a)
+        big = torch.zeros((3, 77, 211), dtype=torch.uint8, device=DEV)
+        view = big[:, 1:76, 5:208]                                                              # pitch 211, offset 5: generic path
+        view.copy_(a)
+        ops.attack_jpeg_requant_(aligned, q)
+        ops.attack_jpeg_requant_(view, q)
+        assert torch.equal(aligned, view), q
+        got = aligned.cpu().numpy()
+        assert np.array_equal(got[:, 72:], base[:, 72:]) and np.array_equal(got[:, :, 200:], base[:, :, 200:])
+        want = attacks.jpeg_requant(base[2], q)
+        assert (np.abs(got[2].astype(np.int16) - want) > 0).mean() < 0.06
