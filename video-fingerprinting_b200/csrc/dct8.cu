@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kDctThreads, kVec ? B200WM_DCT_MASKS_MIN_CTAS 
                 b[8 * y + 4] = mid_biased_byte<0>(rows[y].y); b[8 * y + 5] = mid_biased_byte<1>(rows[y].y);
                 b[8 * y + 6] = mid_biased_byte<2>(rows[y].y); b[8 * y + 7] = mid_biased_byte<3>(rows[y].y);
             }
-            dct8x8<8 * 32768>(b);
+            dct8x8_rows_x2<8 * 32768>(b);
         } else {
             load_block<T>(p, pl.pitch, pl.elem_stride, b);
             dct8x8(b);

@@ -35,6 +35,47 @@ __device__ __forceinline__ void dct8_1d(float& x0, float& x1, float& x2, float& 
     x7 = fmaf(d3, -0.5f * C1, fmaf(d2, 0.5f * C3, fmaf(d1, -0.5f * C5, d0 * (0.5f * C7))));
 }
 
+// Two rows per instruction: dct8_1d() with the two lanes of packed FP32 registers holding the same sample position of
+// two different rows (FFMA2 / FMUL2 / FADD2, sm_100): per lane exactly the scalar operations in the scalar order, so the
+// outputs are bit-identical to two dct8_1d() calls, for half the issue slots.
+__device__ __forceinline__ float2 p2_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 p2_sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }   // b * -1 + a == a - b exactly
+__device__ __forceinline__ float2 p2_mul(float2 a, float k) { return __fmul2_rn(a, make_float2(k, k)); }
+__device__ __forceinline__ float2 p2_fma(float2 a, float k, float2 c) { return __ffma2_rn(a, make_float2(k, k), c); }
+
+template <int kBias8 = 0>
+__device__ __forceinline__ void dct8_1d_x2(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4, float2& x5, float2& x6,
+                                           float2& x7) {
+    const float2 s0 = p2_add(x0, x7), s1 = p2_add(x1, x6), s2 = p2_add(x2, x5), s3 = p2_add(x3, x4);
+    const float2 d0 = p2_sub(x0, x7), d1 = p2_sub(x1, x6), d2 = p2_sub(x2, x5), d3 = p2_sub(x3, x4);
+    const float2 e0 = p2_add(s0, s3), e1 = p2_add(s1, s2), e2 = p2_sub(s1, s2), e3 = p2_sub(s0, s3);
+    const float2 dc = p2_add(e0, e1);
+    x0 = p2_mul(kBias8 ? p2_add(dc, make_float2(-(float)kBias8, -(float)kBias8)) : dc, 0.5f * C4);
+    x4 = p2_mul(p2_sub(e0, e1), 0.5f * C4);
+    x2 = p2_fma(e3, 0.5f * C2, p2_mul(e2, 0.5f * C6));
+    x6 = p2_fma(e3, 0.5f * C6, p2_mul(e2, -0.5f * C2));
+    x1 = p2_fma(d3, 0.5f * C7, p2_fma(d2, 0.5f * C5, p2_fma(d1, 0.5f * C3, p2_mul(d0, 0.5f * C1))));
+    x3 = p2_fma(d3, -0.5f * C5, p2_fma(d2, -0.5f * C1, p2_fma(d1, -0.5f * C7, p2_mul(d0, 0.5f * C3))));
+    x5 = p2_fma(d3, 0.5f * C3, p2_fma(d2, 0.5f * C7, p2_fma(d1, -0.5f * C1, p2_mul(d0, 0.5f * C5))));
+    x7 = p2_fma(d3, -0.5f * C1, p2_fma(d2, 0.5f * C3, p2_fma(d1, -0.5f * C5, p2_mul(d0, 0.5f * C7))));
+}
+
+// 2-D transform with the row pass packed two rows at a time and the column pass scalar: bit-identical to dct8x8()
+template <int kBias8 = 0>
+__device__ __forceinline__ void dct8x8_rows_x2(float (&b)[64]) {
+#pragma unroll
+    for (int yp = 0; yp < 4; ++yp) {
+        float2 r[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) r[x] = make_float2(b[16 * yp + x], b[16 * yp + 8 + x]);
+        dct8_1d_x2<kBias8>(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) { b[16 * yp + x] = r[x].x; b[16 * yp + 8 + x] = r[x].y; }
+    }
+#pragma unroll
+    for (int x = 0; x < 8; ++x) dct8_1d(b[x], b[8 + x], b[16 + x], b[24 + x], b[32 + x], b[40 + x], b[48 + x], b[56 + x]);
+}
+
 // Inverse of dct8_1d (orthonormal DCT-III): x_n = sum_k a_k X_k cos((2n+1) k pi / 16).
 // Even coefficients give a part symmetric in n <-> 7-n, odd coefficients an antisymmetric part.
 __device__ __forceinline__ void idct8_1d(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
