@@ -548,6 +548,9 @@ def main():
     for s in range(batch.n_seg_local):
         pattern, freq, _, _ = result[rank * batch.n_seg_local + s]
         seg_ok += int(pattern is not None and np.array_equal(pattern, batch.payloads[s]))
+    freqs = [result[rank * batch.n_seg_local + s][1] for s in range(batch.n_seg_local)]
+    votes_ok = all(np.array_equal(result[rank * batch.n_seg_local + s][2], batch.payloads[s] * result[rank * batch.n_seg_local + s][3])
+                   for s in range(batch.n_seg_local))
     bits = ops.unpack_bits(batch.raw_bits[:64], batch.block_num)
     raw_acc = float((bits == batch.rows[(np.arange(len(bits)) // SEGMENT_FRAMES)]).mean())
     frame_ok = float((batch.patterns.cpu().numpy() == batch.payloads[np.arange(n_frames) // SEGMENT_FRAMES]).all(axis=1).mean())
@@ -592,6 +595,11 @@ def main():
                     "unaccounted_ms_per_step": ms_per_step - k_embed - k_extract - k_vote,
                     "combine": batch.exchange, "combine_note": getattr(batch, "exchange_note", None),
                     "roofline_fps_per_gpu": peak * 1e9 / (3.0 * W * H)},
+        "config4_hls_segments": {"config": "BASELINE configs[3]: per-segment payload bits (8-bit segment number, 60-frame segments), Counter "
+                                           "vote per segment, state exchanged across the GPUs", "segments_total": batch.n_seg_local * world,
+                                 "segments_on_this_rank": batch.n_seg_local, "most_common_pattern_is_payload": seg_ok / batch.n_seg_local,
+                                 "min_frequency": float(min(f for f in freqs if f is not None)),
+                                 "per_bit_votes_equal_payload_times_frames": bool(votes_ok)},
         "bit_accuracy": {"note": "against the EMBEDDED ground truth; agreement with the reference is in `parity`",
                          "segments_exact": seg_ok / batch.n_seg_local, "frames_exact": frame_ok, "raw_bits_first_64_frames": raw_acc},
     }

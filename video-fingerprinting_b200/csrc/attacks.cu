@@ -91,11 +91,32 @@ __global__ void __launch_bounds__(128) jpeg_requant_kernel(const uint8_t* __rest
     }
 }
 
+// kVec4: width, pitch, frame stride and both base addresses multiples of 4: four samples per thread (one 32-bit load, one
+// 128-bit noise load, one 32-bit store); round half to even by the 1.5 * 2^23 bias, clamp in 16-bit lanes.
+template <bool kVec4>
 __global__ void __launch_bounds__(256) add_noise_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                         const float* __restrict__ noise, long long frame_stride,
                                                         unsigned pitch, int height, int width, int n_frames) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_frame = (long long)height * width;
+    if (kVec4) {
+        const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (i >= per_frame * n_frames) return;
+        const long long f = i / per_frame, p = i - f * per_frame;
+        const int y = (int)(p / width), x = (int)(p - (long long)y * width);
+        const long long o = f * frame_stride + (unsigned long long)y * pitch + x;
+        const unsigned w = *reinterpret_cast<const unsigned*>(src + o);
+        const float4 nz = *reinterpret_cast<const float4*>(noise + i);
+        // (float)sample + noise, one rounding; kept inside the 16-bit lanes of the clamp below whatever the noise is
+        const float b0 = fminf(fmaxf((biased_byte<0>(w) - kBias) + nz.x, -1024.0f), 1024.0f);
+        const float b1 = fminf(fmaxf((biased_byte<1>(w) - kBias) + nz.y, -1024.0f), 1024.0f);
+        const float b2 = fminf(fmaxf((biased_byte<2>(w) - kBias) + nz.z, -1024.0f), 1024.0f);
+        const float b3 = fminf(fmaxf((biased_byte<3>(w) - kBias) + nz.w, -1024.0f), 1024.0f);
+        const unsigned e = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(b0 + kBias), __float_as_uint(b2 + kBias), 0x5410), 0u, 0x00FF00FFu);
+        const unsigned od = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(b1 + kBias), __float_as_uint(b3 + kBias), 0x5410), 0u, 0x00FF00FFu);
+        *reinterpret_cast<unsigned*>(dst + o) = __byte_perm(e, od, 0x6240);
+        return;
+    }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= per_frame * n_frames) return;
     const long long f = i / per_frame, p = i - f * per_frame;
     const int y = (int)(p / width), x = (int)(p - (long long)y * width);
@@ -392,9 +413,16 @@ int launch_attack_noise(const void* src, void* dst, const b200wm_plane* pl, cons
     if (pl->dtype != B200WM_U8 || pl->elem_stride != 1) return B200WM_ERR_UNSUPPORTED;
     const long long n = (long long)pl->height * pl->width * pl->n_frames;
     if (n == 0) return B200WM_OK;
-    add_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const uint8_t*)src, (uint8_t*)dst, noise,
-                                                                      pl->frame_stride_bytes, (unsigned)pl->pitch_bytes,
-                                                                      pl->height, pl->width, pl->n_frames);
+    const bool vec4 = pl->width % 4 == 0 && pl->pitch_bytes % 4 == 0 && pl->frame_stride_bytes % 4 == 0 && (uintptr_t)src % 4 == 0 &&
+                      (uintptr_t)dst % 4 == 0 && (uintptr_t)noise % 16 == 0;
+    if (vec4)
+        add_noise_kernel<true><<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>((const uint8_t*)src, (uint8_t*)dst, noise,
+                                                                                 pl->frame_stride_bytes, (unsigned)pl->pitch_bytes,
+                                                                                 pl->height, pl->width, pl->n_frames);
+    else
+        add_noise_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const uint8_t*)src, (uint8_t*)dst, noise,
+                                                                                  pl->frame_stride_bytes, (unsigned)pl->pitch_bytes,
+                                                                                  pl->height, pl->width, pl->n_frames);
     B200WM_LAUNCH_CHECK("add_noise_kernel");
     return B200WM_OK;
 }
