@@ -217,3 +217,49 @@ def test_fingerprint_payload_schemes_and_decisions():
     assert fp.copy_fingerprint(results) == ([3, 0, 1], "301")
     results[1]["detected_copy_index"] = None
     assert fp.copy_fingerprint(results) == ([None, 0, 1], None)
+
+
+def test_segment_vote_and_packing_properties():
+    """Property tests (hypothesis) of the host logic: SegmentVote.result() reproduces Counter.most_common(1) - ties go to
+    the pattern seen first - for arbitrary pattern lists, orders of arrival and payload lengths; bit packing round-trips;
+    the payload schemes invert."""
+    from hypothesis import given, settings, strategies as st
+    from b200wm import ops
+    from b200wm.vote import SegmentVote
+    from offmark_b200 import fingerprint as fp
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 6).flatmap(lambda L: st.tuples(st.just(L), st.lists(st.integers(0, (1 << L) - 1), min_size=1, max_size=40))),
+           st.randoms(use_true_random=False))
+    def vote_property(case, rnd):
+        L, pats = case
+        vote = SegmentVote(2, L, "cpu")
+        order = list(range(len(pats)))
+        rnd.shuffle(order)                                  # frames arrive in any order; first_seen keeps the frame index
+        for i in order:
+            _fill_vote_state(vote, [pats[i]], [1], [i])
+        want_p, want_f = _reference_vote(pats, L)
+        pattern, freq, votes, frames = vote.result()[1]
+        assert pattern.tolist() == want_p and freq == want_f and frames == len(pats)
+        assert vote.result()[0][0] is None
+        vote.reset()
+        assert vote.result()[1][0] is None and vote.result()[1][3] == 0
+    vote_property()
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 4).flatmap(lambda r: st.integers(1, 200).flatmap(
+        lambda n: st.lists(st.lists(st.integers(0, 1), min_size=n, max_size=n), min_size=r, max_size=r))))
+    def packing_property(rows):
+        packed, n = ops.pack_bits(np.array(rows))
+        assert packed.shape == (len(rows), max(1, (n + 31) // 32)) and packed.dtype == torch.int32
+        assert np.array_equal(ops.unpack_bits(packed, n), np.array(rows, dtype=np.uint8))
+    packing_property()
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.integers(0, 10 ** 6), st.integers(0, 10 ** 6))
+    def payload_property(seg, copy):
+        assert fp.decode_watermark_pattern(o_pay.payload_for_segment_copy(seg, copy)) == (seg % 16, copy % 16)
+        assert int("".join(map(str, fp.generate_payload_for_segment(seg))), 2) == seg % 256
+    payload_property()
+    with pytest.raises(ValueError):
+        ops.pack_bits(np.array([0, 2, 1]))
