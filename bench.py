@@ -811,7 +811,7 @@ def plugin_leg(args, ops, batch, dev, world, pinned_io=False):
         enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity((h, w, 3))))
         if pinned_io:       # the optional batch protocol: batches move from / into the reader's and writer's pinned memory
             sink = BatchWriter(n, (h, w, 3)) if "sink" not in state else state["sink"]
-            sink.count = 0
+            sink.rewind()
             state["sink"] = sink
             Embedder(BatchReader(clip), enc, sink, batch_frames=32).start()
             reader = BatchReader(sink.array)

@@ -375,11 +375,11 @@ def test_batch_reader_writer_protocol_equals_per_frame_flow():
     from offmark_b200.video.extractor import Extractor
     from offmark_b200.video.memory_io import ArrayReader, ArrayWriter, BatchReader, BatchWriter
     from oracle import synth
-    frames = np.stack([synth.random_bgr(128, 192, s) for s in range(7)])
+    frames = np.stack([synth.random_bgr(128, 192, s) for s in range(14)])     # 5 batches of 3: more than the lanes in flight
 
-    def encoder():
+    def encoder(payload=PAYLOAD):
         enc = DwtDctSvdEncoder()
-        enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(frames[0].shape)))
+        enc.read_wm(Shuffler(key=KEY).generate_wm(payload, enc.wm_capacity(frames[0].shape)))
         return enc
     ref_writer = ArrayWriter()
     Embedder(ArrayReader(list(frames)), encoder(), ref_writer).start()                      # per-frame loop
@@ -391,13 +391,17 @@ def test_batch_reader_writer_protocol_equals_per_frame_flow():
         assert len(writer.frames) == len(frames)
         for a, b in zip(ref_writer.frames, writer.frames):
             assert np.array_equal(a, b)
-    marked = np.stack(ref_writer.frames)
+    other = 1 - PAYLOAD                             # second half of the clip carries another payload: order is visible
+    other_writer = ArrayWriter()
+    Embedder(ArrayReader(list(frames[5:])), encoder(other), other_writer).start()
+    marked = np.stack(ref_writer.frames[:5] + other_writer.frames)
     want = Extractor(ArrayReader(list(marked)), DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((8,)))
     want.start()
-    got = Extractor(BatchReader(marked), DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((8,)), batch_frames=4)
-    got.start()
-    assert len(want.patterns) == len(got.patterns) == len(frames)
-    for a, b in zip(want.patterns, got.patterns):
-        assert np.array_equal(a, b) and np.array_equal(a, PAYLOAD)
+    for reader in (BatchReader(marked), BatchReader(torch.from_numpy(marked).pin_memory().numpy())):
+        got = Extractor(reader, DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((8,)), batch_frames=4)
+        got.start()
+        assert len(want.patterns) == len(got.patterns) == len(frames)
+        for k, (a, b) in enumerate(zip(want.patterns, got.patterns)):
+            assert np.array_equal(a, b) and np.array_equal(a, PAYLOAD if k < 5 else other)
     r = BatchReader(frames)                         # the reference's own protocol on the same object
     assert np.array_equal(r.read(), frames[0]) and np.array_equal(r.read_batch(100), frames[1:]) and r.read() is None

@@ -263,3 +263,27 @@ def test_segment_vote_and_packing_properties():
     payload_property()
     with pytest.raises(ValueError):
         ops.pack_bits(np.array([0, 2, 1]))
+
+
+def test_batch_reader_and_writer_bookkeeping():
+    """video/memory_io.py: the reference's read() / write() surface plus the optional batch protocol; reservations are
+    committed in the order they were made and misuse is loud."""
+    from offmark_b200.video.memory_io import BatchReader, BatchWriter
+    frames = np.arange(5 * 4 * 6 * 3, dtype=np.uint8).reshape(5, 4, 6, 3)
+    r = BatchReader(frames)
+    assert (r.height, r.width) == (4, 6)
+    assert np.array_equal(r.read(), frames[0]) and np.array_equal(r.read_batch(100), frames[1:]) and r.read() is None
+    w = BatchWriter(4, frames[0].shape, pinned=False)
+    a, b = w.reserve(2, frames[0].shape), w.reserve(2, frames[0].shape)
+    assert a is not None and b is not None and w.reserve(1, frames[0].shape) is None and len(w.frames) == 0
+    assert w.reserve(1, (4, 6, 1)) is None
+    with pytest.raises(RuntimeError):
+        w.write(frames[0])
+    a[:] = frames[:2]
+    w.commit(2)
+    assert len(w.frames) == 2 and np.array_equal(w.frames, frames[:2])
+    with pytest.raises(RuntimeError):
+        w.commit(3)
+    w.rewind()
+    w.write(frames[4])
+    assert len(w.frames) == 1 and np.array_equal(w.frames[0], frames[4])

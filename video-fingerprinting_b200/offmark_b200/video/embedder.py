@@ -1,4 +1,5 @@
 """B200 drop-in for ``offmark.video.embedder`` (src/offmark/video/embedder.py)."""
+import collections
 import logging
 
 import numpy as np
@@ -8,6 +9,8 @@ from b200wm import ops
 from .._frames import device_of, Staging
 
 logger = logging.getLogger(__name__)
+
+_LANES = 3          # batches in flight in the batch protocol: one uploading, one in the kernel, one downloading
 
 
 class Embedder:
@@ -52,13 +55,28 @@ class Embedder:
             self._flush(pending)
 
     def _run_batches(self):
-        """Readers with the optional batch protocol (video/memory_io.py:BatchReader) hand over ``[n, H, W, 3]`` views."""
+        """Readers with the optional batch protocol (video/memory_io.py:BatchReader) hand over ``[n, H, W, 3]`` views.
+        Up to ``_LANES`` batches are in flight, each on its own stream, so that the upload of batch k+1, the kernel of
+        batch k and the download of batch k-1 overlap; batches are committed to the writer in order."""
+        dev = device_of(self.device)
+        main = torch.cuda.current_stream(dev)
+        lanes = [torch.cuda.Stream(device=dev) for _ in range(_LANES)]
+        inflight = collections.deque()
+        k = 0
         while True:
             frames = self.frame_reader.read_batch(self.batch_frames)
             if frames is None or len(frames) == 0:
                 logger.info('End of input stream')
                 break
-            self._flush_array(np.ascontiguousarray(frames, dtype=np.uint8))
+            if len(inflight) == _LANES:
+                self._retire(inflight.popleft())
+            lane = lanes[k % _LANES]
+            k += 1
+            lane.wait_stream(main)
+            with torch.cuda.stream(lane):
+                inflight.append(self._launch_array(np.ascontiguousarray(frames, dtype=np.uint8), dev, lane))
+        while inflight:
+            self._retire(inflight.popleft())
 
     def _flush(self, pending):
         """One upload, one fused kernel launch and one download for the whole batch; frames are written
@@ -75,18 +93,24 @@ class Embedder:
                 self.frame_writer.write(f)
         pending.clear()
 
-    def _flush_array(self, frames):
-        """A batch that is already one ``[n, H, W, 3]`` array: one copy up (asynchronous and at link speed when the
-        reader's memory is pinned), one launch, one copy down - straight into the writer's memory when it offers
-        ``reserve`` / ``commit``."""
-        dev = device_of(self.device)
+    def _launch_array(self, frames, dev, lane):
+        """A batch that is already one ``[n, H, W, 3]`` array, on the current stream ``lane``: one copy up (asynchronous
+        and at link speed when the reader's memory is pinned), one launch, one copy down - straight into the writer's
+        memory when it offers ``reserve`` / ``commit``.  Returns what ``_retire`` needs to hand the batch over."""
         host = torch.from_numpy(frames)
         marked = self.frame_embedder.mark_rgb8(host.to(dev, non_blocking=host.is_pinned()))
         dest = self.frame_writer.reserve(len(frames), frames.shape[1:]) if hasattr(self.frame_writer, "reserve") else None
         if dest is not None:
             torch.from_numpy(dest).copy_(marked, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            self.frame_writer.commit(len(frames))
+        done = torch.cuda.Event()
+        done.record(lane)
+        return done, len(frames), dest, marked
+
+    def _retire(self, batch):
+        done, n, dest, marked = batch
+        done.synchronize()
+        if dest is not None:
+            self.frame_writer.commit(n)
             return
         for f in self._staging.download(marked):
             self.frame_writer.write(f)

@@ -1,4 +1,5 @@
 """B200 drop-in for ``offmark.video.extractor`` (src/offmark/video/extractor.py)."""
+import collections
 import logging
 
 import numpy as np
@@ -8,6 +9,8 @@ from b200wm import ops
 from .._frames import device_of, Staging
 
 logger = logging.getLogger(__name__)
+
+_LANES = 2          # batches in flight in the batch protocol: one uploading while the other is read and voted
 
 
 class Extractor:
@@ -52,18 +55,38 @@ class Extractor:
             self._flush(pending)
 
     def _run_batches(self):
-        """Readers with the optional batch protocol (video/memory_io.py:BatchReader) hand over ``[n, H, W, 3]`` views."""
+        """Readers with the optional batch protocol (video/memory_io.py:BatchReader) hand over ``[n, H, W, 3]`` views.
+        ``_LANES`` batches are in flight on their own streams (the upload of batch k+1 overlaps the kernels of batch
+        k); patterns are logged in frame order."""
+        dev = device_of(self.device)
+        main = torch.cuda.current_stream(dev)
+        lanes = [torch.cuda.Stream(device=dev) for _ in range(_LANES)]
+        inflight = collections.deque()
+        k = 0
         while True:
             frames = self.frame_reader.read_batch(self.batch_frames)
             if frames is None or len(frames) == 0:
                 logger.info('End of input stream')
                 break
             if self.frame_extractor.scales[1] <= 0:
+                while inflight:
+                    self._log_batch(inflight.popleft())
                 for f in frames:
                     self._log(self.check_frame(f))
                 continue
-            host = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.uint8))
-            self._vote_batch(host.to(device_of(self.device), non_blocking=host.is_pinned()))
+            if len(inflight) == _LANES:
+                self._log_batch(inflight.popleft())
+            lane = lanes[k % _LANES]
+            k += 1
+            lane.wait_stream(main)
+            with torch.cuda.stream(lane):
+                host = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.uint8))
+                patterns = self._launch_vote(host.to(dev, non_blocking=host.is_pinned()))
+                done = torch.cuda.Event()
+                done.record(lane)
+            inflight.append((done, patterns))
+        while inflight:
+            self._log_batch(inflight.popleft())
 
     def _log(self, pattern):
         self.patterns.append(pattern)
@@ -82,15 +105,27 @@ class Extractor:
             self._vote_batch(self._staging.upload(group, dev))
         pending.clear()
 
-    def _vote_batch(self, frames):
-        """uint8 ``[n, H, W, 3]`` CUDA frames -> one fused extract launch, one vote launch, n logged patterns."""
+    def _launch_vote(self, frames):
+        """uint8 ``[n, H, W, 3]`` CUDA frames -> one fused extract launch and one vote launch on the current stream;
+        returns the ``[n, payload_len]`` patterns (device)."""
         h, w = frames.shape[1], frames.shape[2]
         raw, counts = ops.dwtsvd_extract_rgb8(frames, scale=self.frame_extractor.scales[1], channel=1,
                                               payload_len=self.degenerator.payload_len)
         patterns, _ = self.degenerator.degenerate_counts(counts, h * w // 64)
+        return patterns
+
+    def _log_batch(self, batch):
+        done, patterns = batch
+        done.synchronize()
         fmt = getattr(self.degenerator, "format_pattern", None)
         for p in patterns.cpu().numpy():
             self._log(fmt(p) if fmt else p)
+
+    def _vote_batch(self, frames):
+        done = torch.cuda.Event()
+        patterns = self._launch_vote(frames)
+        done.record()
+        self._log_batch((done, patterns))
 
     def check_frame(self, frame_rgb):
         dev = device_of(self.device)

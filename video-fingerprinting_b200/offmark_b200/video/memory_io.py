@@ -61,28 +61,41 @@ class BatchReader:
 class BatchWriter:
     """Writer into one preallocated ``[N, H, W, 3]`` uint8 array (pinned by default).  OPTIONAL batch protocol:
     ``reserve(n, frame_shape)`` hands out the view the next ``n`` frames are to be written into (the driver downloads from
-    the GPU straight into it), ``commit(n)`` publishes them.  ``write(frame)`` works as in the reference (one copy)."""
+    the GPU straight into it), ``commit(n)`` publishes them; several reservations may be outstanding and are committed in
+    the order they were made.  ``write(frame)`` works as in the reference (one copy)."""
 
     def __init__(self, n_frames, frame_shape, pinned=True):
         import torch
         self._store = torch.empty((n_frames,) + tuple(frame_shape), dtype=torch.uint8, pin_memory=pinned)
         self.array = self._store.numpy()
-        self.count = 0
+        self.count = 0                 # frames committed
+        self._reserved = 0             # frames handed out by reserve() (>= count)
 
     @property
     def frames(self):
         return self.array[:self.count]
 
+    def rewind(self):
+        """Start over at frame 0 (the store is reused)."""
+        self.count = self._reserved = 0
+
     def write(self, frame):
+        if self._reserved != self.count:
+            raise RuntimeError("BatchWriter.write() with reservations outstanding")
         self.array[self.count] = frame
         self.count += 1
+        self._reserved = self.count
 
     def reserve(self, n, frame_shape):
-        if tuple(frame_shape) != self.array.shape[1:] or self.count + n > len(self.array):
+        if tuple(frame_shape) != self.array.shape[1:] or self._reserved + n > len(self.array):
             return None
-        return self.array[self.count:self.count + n]
+        view = self.array[self._reserved:self._reserved + n]
+        self._reserved += n
+        return view
 
     def commit(self, n):
+        if self.count + n > self._reserved:
+            raise RuntimeError("BatchWriter.commit() of more frames than were reserved")
         self.count += n
 
     def close(self):
