@@ -796,7 +796,7 @@ def plugin_leg(args, ops, batch, dev, world, pinned_io=False):
 
     class Sink:                                          # consumes a frame inside write(), like the ffmpeg pipe
         def __init__(self):
-            self.array = np.empty((n, h, w, 3), dtype=np.uint8)
+            self.array = np.zeros((n, h, w, 3), dtype=np.uint8)      # touched once: write() is a warm copy
             self.k = 0
 
         def write(self, f):
@@ -816,7 +816,10 @@ def plugin_leg(args, ops, batch, dev, world, pinned_io=False):
             Embedder(BatchReader(clip), enc, sink, batch_frames=32).start()
             reader = BatchReader(sink.array)
         else:               # the reference's read() / write() per frame on pageable arrays
-            sink = Sink()
+            if "sink" not in state:
+                state["sink"] = Sink()
+            sink = state["sink"]
+            sink.k = 0
             Embedder(ArrayReader(list(clip)), enc, sink, batch_frames=32).start()
             reader = ArrayReader(list(sink.array))
         ex = Extractor(reader, DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((PAYLOAD_LEN,)), batch_frames=32)
@@ -827,8 +830,8 @@ def plugin_leg(args, ops, batch, dev, world, pinned_io=False):
     ok = float(np.mean([np.array_equal(p, PAYLOAD) for p in patterns]))
     how = ("BatchReader / BatchWriter over pinned arrays (optional batch protocol: whole batches move from / into the reader's and "
            "writer's memory)" if pinned_io else
-           "pageable rgb24 numpy frames through per-frame read() / write() (uploads staged through pinned buffers by copy threads; the "
-           "sink copies every frame, as a pipe would)")
+           "pageable rgb24 numpy frames through per-frame read() / write() (uploads staged through pinned buffers by copy threads, "
+           "three batches in flight: gather, GPU, write; the sink copies every frame into a preallocated array, as a pipe would)")
     return {"value": fps, "unit": "frames/s", "frames_per_gpu": n, "steps": 2, "h2d_bytes_per_step": 2 * n * h * w * 3,
             "d2h_bytes_per_step": n * h * w * 3 + n * PAYLOAD_LEN, "frames_exact": ok,
             "path": "offmark_b200 Embedder(batch_frames=32).start() + Extractor(batch_frames=32).start(), fused rgb24 kernels, " + how}

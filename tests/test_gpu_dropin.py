@@ -170,18 +170,52 @@ def test_embedder_batched_mode_equals_per_frame_mode(golden_dir):
     from offmark_b200.video.embedder import Embedder
     from offmark_b200.video.memory_io import ArrayReader, ArrayWriter
     from oracle import synth
-    frames = [synth.random_bgr(64, 96, s) for s in range(7)]
+    frames = [synth.random_bgr(64, 96, s) for s in range(17)]            # 6 batches of 3: the three-slot pipeline wraps
 
-    def run(batch):
+    def run(batch, clip=frames):
         enc = DwtDctSvdEncoder()
-        enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(frames[0].shape)))
+        enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(clip[0].shape)))
         w = ArrayWriter()
-        Embedder(ArrayReader([f.copy() for f in frames]), enc, w, batch_frames=batch).start()
+        Embedder(ArrayReader([f.copy() for f in clip]), enc, w, batch_frames=batch).start()
         return w.frames
     one, many = run(1), run(3)
     assert len(one) == len(many) == len(frames)
     for a, b in zip(one, many):
         assert a.dtype == np.uint8 and np.array_equal(a, b)
+    # frames above 1 MiB are gathered by the copy threads; 22 frames in batches of 4 (ragged end)
+    big = [synth.random_bgr(512, 704, 100 + s) for s in range(22)]
+    one, many = run(1, big), run(4, big)
+    assert len(one) == len(many) == len(big)
+    for a, b in zip(one, many):
+        assert np.array_equal(a, b)
+
+
+def test_embedder_batched_mode_cuts_batches_where_the_frame_shape_changes():
+    """A batch is one launch, so it holds one shape: a clip whose geometry changes mid-stream is cut there (the reference's
+    loop has no such restriction, embedder.py:19-27) and the marked frames still equal the per-frame path's, in order."""
+    from offmark_b200.embed.dwt_dct_svd_encoder import DwtDctSvdEncoder
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.video.embedder import Embedder
+    from offmark_b200.video.memory_io import ArrayReader, ArrayWriter
+    from offmark_b200._frames import gathered_batches
+    from oracle import synth
+    shapes = [(64, 96)] * 4 + [(96, 64)] * 2 + [(64, 96)] * 5
+    frames = [synth.random_bgr(h, w, s) for s, (h, w) in enumerate(shapes)]
+    assert [len(g) for g in gathered_batches(ArrayReader(frames), 3)] == [3, 1, 2, 3, 2]
+
+    def run(batch):
+        w = ArrayWriter()
+
+        class PerShapeEncoder(DwtDctSvdEncoder):                 # the watermark is tiled to the frame's capacity
+            def mark_rgb8(self, f):
+                self.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, self.wm_capacity(f.shape[-3:])))
+                return super().mark_rgb8(f)
+        Embedder(ArrayReader([f.copy() for f in frames]), PerShapeEncoder(), w, batch_frames=batch).start()
+        return w.frames
+    one, many = run(1), run(3)
+    assert len(one) == len(many) == len(frames)
+    for a, b in zip(one, many):
+        assert a.shape == b.shape and np.array_equal(a, b)
 
 
 def test_extractor_batched_mode_equals_per_frame_mode():
@@ -193,11 +227,12 @@ def test_extractor_batched_mode_equals_per_frame_mode():
     from offmark_b200.video.extractor import Extractor
     from offmark_b200.video.memory_io import ArrayReader, ArrayWriter
     from oracle import synth
-    frames = [synth.random_bgr(128, 192, s) for s in range(5)]
-    enc = DwtDctSvdEncoder()
-    enc.read_wm(Shuffler(key=KEY).generate_wm(PAYLOAD, enc.wm_capacity(frames[0].shape)))
+    frames = [synth.random_bgr(128, 192, s) for s in range(9)]
     w = ArrayWriter()
-    Embedder(ArrayReader(frames), enc, w, batch_frames=4).start()
+    for part, payload in ((frames[:4], PAYLOAD), (frames[4:], 1 - PAYLOAD)):     # two payloads: the order of the patterns is visible
+        enc = DwtDctSvdEncoder()
+        enc.read_wm(Shuffler(key=KEY).generate_wm(payload, enc.wm_capacity(frames[0].shape)))
+        Embedder(ArrayReader(part), enc, w, batch_frames=4).start()
 
     def run(batch):
         ex = Extractor(ArrayReader(w.frames), DwtDctSvdDecoder(), DeShuffler(key=KEY).set_shape((8,)), batch_frames=batch)
@@ -205,8 +240,8 @@ def test_extractor_batched_mode_equals_per_frame_mode():
         return ex.patterns
     one, many = run(1), run(2)
     assert len(one) == len(many) == len(frames)
-    for a, b in zip(one, many):
-        assert np.array_equal(a, b) and np.array_equal(a, PAYLOAD)
+    for k, (a, b) in enumerate(zip(one, many)):
+        assert np.array_equal(a, b) and np.array_equal(a, PAYLOAD if k < 4 else 1 - PAYLOAD)
 
 
 def test_fingerprint_layer_copy_sequence_roundtrip():

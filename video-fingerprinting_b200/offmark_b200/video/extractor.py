@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from b200wm import ops
-from .._frames import device_of, Staging
+from .._frames import device_of, gathered_batches, Staging
 
 logger = logging.getLogger(__name__)
 
@@ -24,35 +24,59 @@ class Extractor:
         self.device = device
         self.batch_frames = max(1, int(batch_frames))      # optional extension: frames per kernel launch
         self.patterns = []                                 # optional extension: every pattern that was logged
-        self._staging = Staging()
+        self._slots = [Staging() for _ in range(_LANES)]   # pinned staging, one per batch in flight
 
     def start(self):
         logger.debug('Entering start()')
-        batched = (self.batch_frames > 1 and hasattr(self.frame_extractor, "decode_rgb8")
-                   and hasattr(self.degenerator, "degenerate_counts"))
-        if batched and hasattr(self.frame_reader, "read_batch"):
-            self._run_batches()
-        else:
-            self._run_frames(batched)
+        try:
+            batched = (self.batch_frames > 1 and hasattr(self.frame_extractor, "decode_rgb8")
+                       and hasattr(self.degenerator, "degenerate_counts") and self.frame_extractor.scales[1] > 0)
+            if batched and hasattr(self.frame_reader, "read_batch"):
+                self._run_batches()
+            elif batched:
+                self._run_gathered()
+            else:
+                self._run_frames()
+        except BaseException:
+            try:                                   # copies may still be in flight into the staging buffers
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            raise
+        finally:
+            for slot in self._slots:
+                slot.release()
         self.frame_reader.close()
         logger.info('Done')
 
-    def _run_frames(self, batched):
-        """The reference's loop (extractor.py:19-26): one ``read()`` per frame; batched mode gathers ``batch_frames`` of them."""
-        pending = []
+    def _run_frames(self):
+        """The reference's loop (extractor.py:19-26), one frame at a time."""
         while True:
             in_frame = self.frame_reader.read()
             if in_frame is None:
                 logger.info('End of input stream')
                 break
-            if not batched:
-                self._log(self.check_frame(in_frame))
-                continue
-            pending.append(np.ascontiguousarray(in_frame, dtype=np.uint8))
-            if len(pending) == self.batch_frames:
-                self._flush(pending)
-        if pending:
-            self._flush(pending)
+            self._log(self.check_frame(in_frame))
+
+    def _run_gathered(self):
+        """The reference's ``read()`` per frame, ``batch_frames`` of them per launch (one fused extract launch and one
+        vote launch), two batches in flight: the copy threads gather batch k into pinned memory while the GPU uploads
+        and reads batch k-1.  The patterns are logged in frame order and equal the per-frame path's."""
+        dev = device_of(self.device)
+        staged = None
+        for k, group in enumerate(gathered_batches(self.frame_reader, self.batch_frames)):
+            fresh = self._slots[k % _LANES].stage(group)
+            if staged:
+                self._vote_staged(staged, dev)
+            staged = fresh
+        logger.info('End of input stream')
+        if staged:
+            self._vote_staged(staged, dev)
+
+    def _vote_staged(self, staged, dev):
+        host, futures = staged
+        Staging.settle(futures)
+        self._vote_batch(host.to(dev, non_blocking=True))
 
     def _run_batches(self):
         """Readers with the optional batch protocol (video/memory_io.py:BatchReader) hand over ``[n, H, W, 3]`` views.
@@ -68,12 +92,6 @@ class Extractor:
             if frames is None or len(frames) == 0:
                 logger.info('End of input stream')
                 break
-            if self.frame_extractor.scales[1] <= 0:
-                while inflight:
-                    self._log_batch(inflight.popleft())
-                for f in frames:
-                    self._log(self.check_frame(f))
-                continue
             if len(inflight) == _LANES:
                 self._log_batch(inflight.popleft())
             lane = lanes[k % _LANES]
@@ -91,19 +109,6 @@ class Extractor:
     def _log(self, pattern):
         self.patterns.append(pattern)
         logger.info(pattern)
-
-    def _flush(self, pending):
-        """One upload, one fused extract launch and one vote launch for the whole batch; the patterns are
-        logged in frame order and equal the per-frame path's."""
-        dev = device_of(self.device)
-        same = all(f.shape == pending[0].shape for f in pending)
-        for group in ([pending] if same else [[f] for f in pending]):
-            if self.frame_extractor.scales[1] <= 0:
-                for f in group:
-                    self._log(self.check_frame(f))
-                continue
-            self._vote_batch(self._staging.upload(group, dev))
-        pending.clear()
 
     def _launch_vote(self, frames):
         """uint8 ``[n, H, W, 3]`` CUDA frames -> one fused extract launch and one vote launch on the current stream;
