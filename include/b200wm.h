@@ -220,6 +220,8 @@ B200WM_API int b200wm_vote_counts(const uint32_t* raw_bits, int32_t n_frames, in
  * packed   [n_frames] uint64 (nullable; payload_len <= 64; payload bit j at bit position payload_len-1-j,
  *          i.e. the integer whose binary string is the pattern string of
  *          tests/segment_mark_detect_hls.py:145).
+ * perm [payload_len] must be a permutation of 0..payload_len-1; an entry outside that range is skipped (nothing is
+ * written for it), the host-buffer entry points reject such a table with B200WM_ERR_INVALID.
  */
 B200WM_API int b200wm_vote_finish(const int32_t* pos_counts, int32_t n_frames, int32_t payload_len,
                        int64_t block_num, const int32_t* perm,
@@ -235,6 +237,7 @@ B200WM_API int b200wm_vote_finish(const int32_t* pos_counts, int32_t n_frames, i
  * first_seen [n_segments, 2^payload_len] int32, min-accumulated (caller fills with INT32_MAX)
  * bit_votes  [n_segments, payload_len]   int32, accumulated: frames voting 1 per payload bit
  * seg_frames [n_segments]                int32, accumulated: frames per segment
+ * Frames whose segment is outside [0, n_segments) or whose packed pattern has bits above payload_len are ignored.
  */
 B200WM_API int b200wm_pattern_hist(const uint64_t* packed, const int32_t* frame_segment,
                         const int32_t* frame_order, int32_t order_offset,

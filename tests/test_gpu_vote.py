@@ -184,3 +184,55 @@ def test_symmetric_segment_vote_in_a_one_rank_group():
             assert torch.equal(plain.first_seen.reshape(-1), fused.first_seen.reshape(-1))
     finally:
         dist.destroy_process_group()
+
+
+def test_pattern_hist_ignores_what_is_out_of_range_and_rejects_wrong_types():
+    """The histogram kernels read 8 bytes per frame: anything but int64 patterns is refused by the wrapper, and a frame
+    whose segment or pattern is out of range is skipped by the kernel instead of writing outside the tables."""
+    from b200wm import ops
+    from b200wm.vote import SegmentVote
+    L, n_seg = 8, 2
+    packed = torch.tensor([3, 300, 5, 3, -1], dtype=torch.int64, device=DEV)          # 300 and -1 are not 8-bit patterns
+    seg = torch.tensor([0, 0, 9, 1, 1], dtype=torch.int32, device=DEV)                # 9 is not a segment
+    st = ops.pattern_hist(packed, L, n_seg, seg)
+    torch.cuda.synchronize()
+    assert st["seg_frames"].tolist() == [1, 1] and int(st["hist"].sum()) == 2
+    assert int(st["hist"][0, 3]) == 1 and int(st["hist"][1, 3]) == 1
+    assert st["first_seen"][0, 3].item() == 0 and st["first_seen"][1, 3].item() == 3
+    res = SegmentVote(n_seg, L, DEV).add(packed, frame_segment=seg.to(torch.int64)).result()       # coerced to int32
+    assert [r[1] for r in res] == [1, 1]
+    with pytest.raises(ValueError):
+        ops.pattern_hist(packed.to(torch.int32), L, n_seg, seg)
+    with pytest.raises(ValueError):
+        ops.pattern_hist(packed, L, n_seg, seg.to(torch.int64))
+    with pytest.raises(ValueError):
+        ops.pattern_hist(packed, L, n_seg, seg[:3].contiguous())
+    with pytest.raises(ValueError):
+        ops.pattern_hist(packed.cpu(), L, n_seg, None)
+    with pytest.raises(ValueError):
+        ops.pattern_hist(packed, 17, n_seg, seg)
+
+
+def test_a_table_that_is_not_a_permutation_never_writes_outside_the_patterns():
+    """``perm`` lives on the GPU for b200wm_vote_finish, so its entries are guarded in the kernel (an entry that is not
+    a payload position is skipped); the host-buffer entry points see the table and refuse it."""
+    from b200wm import ops
+    L, n = 8, 4
+    counts = torch.full((n, L), 3, dtype=torch.int32, device=DEV)
+    counts[:, 2] = 9
+    perm = torch.tensor([0, 1, 2, 3, 99, -5, 6, 7], dtype=torch.int32, device=DEV)
+    patterns, _ = ops.vote_finish(counts, 10 * L, perm)
+    good, _ = ops.vote_finish(counts, 10 * L, torch.arange(L, dtype=torch.int32, device=DEV))
+    torch.cuda.synchronize()
+    keep = [0, 1, 2, 3, 6, 7]
+    assert torch.equal(patterns[:, keep], good[:, keep]) and good[:, 2].tolist() == [1] * n
+    planes = np.zeros((2, 64, 64), dtype=np.uint8)
+    with pytest.raises(ValueError):
+        ops.dwtsvd_detect_host(planes, np.array([0, 1, 2, 3, 4, 5, 6, 8], dtype=np.int32))
+    rows = ops.pack_bits(np.zeros((1, 64), dtype=np.int64))[0].cpu().contiguous()
+    with pytest.raises(ValueError):
+        ops.dwtsvd_mark_verify_host(planes, np.empty_like(planes), rows, np.array([0, 1, 2, 3, 4, 5, 6, -1], dtype=np.int32), wm_len=64)
+    with pytest.raises(ValueError):
+        ops.vote_counts(torch.zeros((2, 2), dtype=torch.int64, device=DEV), 64, 8)
+    with pytest.raises(ValueError):
+        ops.vote_counts(torch.zeros((2, 2), dtype=torch.int32, device=DEV), 65, 8)

@@ -305,7 +305,11 @@ def dct8_decode(lum, planes, alpha=20.0, payload_len=None, lum_channel=None, cha
 # ----------------------------------------------------------------------------- votes
 def vote_counts(raw_bits, block_num, payload_len):
     require_cuda()
+    if raw_bits.dtype != torch.int32 or raw_bits.dim() != 2 or not raw_bits.is_cuda or not raw_bits.is_contiguous():
+        raise ValueError("raw_bits must be a contiguous CUDA int32 [N, words] tensor")
     n, words = raw_bits.shape
+    if int(payload_len) <= 0 or not 0 <= int(block_num) <= 32 * words:
+        raise ValueError("payload_len must be positive and block_num within the packed words")
     counts = torch.empty((n, payload_len), dtype=torch.int32, device=raw_bits.device)
     check(lib.b200wm_vote_counts(_ptr(raw_bits), n, words, int(block_num), int(payload_len), _ptr(counts), _stream()))
     return counts
@@ -314,9 +318,11 @@ def vote_counts(raw_bits, block_num, payload_len):
 def vote_finish(pos_counts, block_num, perm):
     """Per-frame finish of DeShuffler.degenerate -> (patterns uint8 [N, L], packed int64 [N] or None)."""
     require_cuda()
+    if pos_counts.dtype != torch.int32 or pos_counts.dim() != 2 or not pos_counts.is_cuda or not pos_counts.is_contiguous():
+        raise ValueError("pos_counts must be a contiguous CUDA int32 [N, payload_len] tensor")
     n, length = pos_counts.shape
-    if perm.dtype != torch.int32 or perm.numel() != length or not perm.is_cuda:
-        raise ValueError("perm must be a CUDA int32 tensor of payload_len entries")
+    if perm.dtype != torch.int32 or perm.numel() != length or not perm.is_cuda or not perm.is_contiguous():
+        raise ValueError("perm must be a contiguous CUDA int32 tensor of payload_len entries")
     patterns = torch.empty((n, length), dtype=torch.uint8, device=pos_counts.device)
     packed = torch.empty((n,), dtype=torch.int64, device=pos_counts.device) if length <= 64 else None
     check(lib.b200wm_vote_finish(_ptr(pos_counts), n, length, int(block_num), _ptr(perm), _ptr(patterns), _ptr(packed),
@@ -327,10 +333,27 @@ def vote_finish(pos_counts, block_num, perm):
 INT32_MAX = 2 ** 31 - 1
 
 
+def _check_hist_inputs(packed, payload_len, frame_segment, frame_order):
+    """The histogram kernels read 8 bytes per frame from ``packed`` and 4 from the per-frame tables."""
+    if not isinstance(packed, torch.Tensor) or not packed.is_cuda or packed.dtype != torch.int64 or packed.dim() != 1 \
+            or not packed.is_contiguous():
+        raise ValueError("packed must be a contiguous 1-D CUDA int64 tensor (the second result of vote_finish)")
+    if not 1 <= int(payload_len) <= 16:
+        raise ValueError("payload_len must be 1..16 for the pattern histogram (gathered_pattern_vote takes any length)")
+    for name, t in (("frame_segment", frame_segment), ("frame_order", frame_order)):
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or t.device != packed.device or t.dtype != torch.int32 or not t.is_contiguous() \
+                or t.numel() != packed.numel():
+            raise ValueError(f"{name} must be a contiguous int32 tensor on packed's device with one entry per frame")
+
+
 def pattern_hist(packed, payload_len, n_segments=1, frame_segment=None, frame_order=None, order_offset=0, state=None):
     """Accumulate the device half of the cross-frame vote.  ``state`` (from a previous call) is
-    updated in place.  -> dict(hist, first_seen, bit_votes, seg_frames)."""
+    updated in place.  -> dict(hist, first_seen, bit_votes, seg_frames).  Frames whose segment is outside
+    ``[0, n_segments)`` or whose pattern has bits above ``payload_len`` are ignored."""
     require_cuda()
+    _check_hist_inputs(packed, payload_len, frame_segment, frame_order)
     dev = packed.device
     if state is None:
         state = {
@@ -351,6 +374,7 @@ def pattern_hist_publish(packed, payload_len, n_segments, state, frame_segment, 
     """``pattern_hist`` into ``state`` (views of this rank's block) fused with the NVLink exchange of the block
     (``b200wm_pattern_hist_publish``).  ``peers_dev``: device address of the array of peer base pointers."""
     require_cuda()
+    _check_hist_inputs(packed, payload_len, frame_segment, frame_order)
     check(lib.b200wm_pattern_hist_publish(_ptr(packed), _ptr(frame_segment), _ptr(frame_order), int(order_offset), packed.numel(),
                                           int(payload_len), int(n_segments), _ptr(state["hist"]), _ptr(state["first_seen"]),
                                           _ptr(state["bit_votes"]), _ptr(state["seg_frames"]), C.c_void_p(int(peers_dev)),

@@ -134,6 +134,10 @@ class SegmentVote:
         ``frame_segment`` holds global segment numbers (owned mode: all inside this rank's block)."""
         state, first = self._mine()
         n_seg = self.owned[1] if self.owned else self.n_segments
+        if frame_segment is not None and frame_segment.dtype != torch.int32:
+            frame_segment = frame_segment.to(torch.int32)
+        if frame_order is not None and frame_order.dtype != torch.int32:
+            frame_order = frame_order.to(torch.int32)
         if first and frame_segment is not None:
             frame_segment = frame_segment - first
         if self._symm is not None:

@@ -206,11 +206,19 @@ int mark_host(const uint8_t* src, uint8_t* dst, const b200wm_plane* pl, const ui
     return rc ? rc : rc_sync;
 }
 
+// The de-shuffling table scatters vote j to payload position perm[j]: every entry must be a position.
+static bool perm_in_range(const int32_t* perm_host, int payload_len) {
+    for (int j = 0; j < payload_len; ++j)
+        if (perm_host[j] < 0 || perm_host[j] >= payload_len) return false;
+    return true;
+}
+
 int detect_host(const uint8_t* src, const b200wm_plane* pl, float scale, int payload_len, const int32_t* perm_host,
                 uint8_t* patterns_host, uint32_t* raw_bits_host, int32_t* pos_counts_host, int chunk_frames) {
     int rc = check_host_plane(pl);
     if (rc) return rc;
     if (!src || !perm_host || !patterns_host || payload_len <= 0) return B200WM_ERR_INVALID;
+    if (!perm_in_range(perm_host, payload_len)) return B200WM_ERR_INVALID;
     if (pl->n_frames == 0) return B200WM_OK;
     const int chunk = pick_chunk(chunk_frames, pl);
     const size_t plane = (size_t)pl->width * pl->height;
@@ -285,6 +293,7 @@ int mark_verify_host(const uint8_t* src, uint8_t* dst, const b200wm_plane* pl, c
     if (frame_row_host)
         for (int f = 0; f < pl->n_frames; ++f)
             if (frame_row_host[f] < 0 || frame_row_host[f] >= n_rows) return B200WM_ERR_INVALID;
+    if (!perm_in_range(perm_host, payload_len)) return B200WM_ERR_INVALID;
     if (pl->n_frames == 0) return B200WM_OK;
     const int chunk = pick_chunk(chunk_frames, pl);
     const size_t plane = (size_t)pl->width * pl->height;

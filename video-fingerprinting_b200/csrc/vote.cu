@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(128) vote_finish_kernel(const int32_t* __restr
         const long long n = i < block_num ? (block_num - i + L - 1) / L : 0;
         const int bit = (!empty && n > 0 && (double)cnt[i] / (double)n > thr) ? 1 : 0;
         const int j = perm[i];
+        if ((unsigned)j >= (unsigned)L) continue;          // not an index into the payload: nothing is written for it
         patterns[(long long)warp * L + j] = (uint8_t)bit;
         if (L <= 64 && bit) word |= 1ull << (L - 1 - j);
     }
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) pattern_hist_kernel(const unsigned long l
     const int seg = frame_segment ? frame_segment[f] : 0;
     if (seg < 0 || seg >= n_segments) return;
     const unsigned long long p = packed[f];
+    if (p >> L) return;                       // not a pattern of L bits: ignored like a frame of no segment
     const long long bin = (long long)seg * (1ll << L) + (long long)p;
     atomicAdd(&hist[bin], 1);
     atomicMin(&first_seen[bin], frame_order ? frame_order[f] : order_offset + f);
@@ -184,8 +186,8 @@ __device__ __forceinline__ void hist_and_ticket(const unsigned long long* __rest
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < n_frames) {
         const int seg = frame_segment ? frame_segment[f] : 0;
-        if (seg >= 0 && seg < n_segments) {
-            const unsigned long long p = packed[f];
+        const unsigned long long p = packed[f];
+        if (seg >= 0 && seg < n_segments && (p >> L) == 0) {
             const long long bin = (long long)seg * (1ll << L) + (long long)p;
             atomicAdd(&hist[bin], 1);
             atomicMin(&first_seen[bin], frame_order ? frame_order[f] : order_offset + f);
