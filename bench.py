@@ -744,6 +744,9 @@ def _run_e2e(args, ops, batch, dev, world):
 
     def timed_copy(up, down):
         torch.cuda.synchronize()
+        if world > 1:                   # every rank copies at the same time: the probe sees the box's shared host side
+            import torch.distributed as dist
+            dist.barrier()
         t0 = time.perf_counter()
         if up:
             scratch.copy_(host_in[:m], non_blocking=True)
@@ -754,7 +757,8 @@ def _run_e2e(args, ops, batch, dev, world):
         return m * h * w / (time.perf_counter() - t0) / 1e9
     timed_copy(True, True)
     link = {"h2d_GBs": round(timed_copy(True, False), 1), "d2h_GBs": round(timed_copy(False, True), 1),
-            "each_way_GBs_when_both": round(timed_copy(True, True), 1)}
+            "each_way_GBs_when_both": round(timed_copy(True, True), 1),
+            "note": "plain pinned copies of 500 frames on rank 0, all ranks copying at the same time (barrier before each)"}
     del scratch
     out = {
         "e2e": {"value": fps1, "unit": "frames/s", "h2d_bytes_per_step": n * h * w, "d2h_bytes_per_step": n * h * w + n * PAYLOAD_LEN,
