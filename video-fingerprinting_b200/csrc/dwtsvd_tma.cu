@@ -39,6 +39,7 @@
 // per row, base and frame stride multiples of 16 bytes, and either tight rows of at most 256 tiles (any
 // parity) or 16-byte aligned rows with an even number of tiles; rows of 129..183 tiles are left to the
 // vectorised-load kernels, which measured faster there.
+#include <cstdlib>
 #include <mutex>
 #include "common.cuh"
 #include "svd4.cuh"
@@ -60,6 +61,9 @@ constexpr int kEmbedStages = B200WM_EMBED_STAGES;      // >= 3: load in flight +
 #endif
 #ifndef B200WM_EMBED_MIN_CTAS
 #define B200WM_EMBED_MIN_CTAS 3
+#endif
+#ifndef B200WM_EMBED_WIDE_CTAS
+#define B200WM_EMBED_WIDE_CTAS 2
 #endif
 constexpr int kExtractStages = B200WM_EXTRACT_STAGES;
 
@@ -356,7 +360,7 @@ dwtsvd_extract_tma_kernel(const uint8_t* __restrict__ src, ExtractArgs ex, Strip
 
 // ---- embed ----------------------------------------------------------------------------------------------
 template <bool kWhole, bool kNarrow, unsigned kPitch, int kCW>
-__global__ void __launch_bounds__((kCW + 1) * 32, kCW == 3 ? B200WM_EMBED_MIN_CTAS + 1 : B200WM_EMBED_MIN_CTAS)
+__global__ void __launch_bounds__((kCW + 1) * 32, kCW == 3 ? B200WM_EMBED_MIN_CTAS + 1 : (kCW == 8 ? B200WM_EMBED_WIDE_CTAS : B200WM_EMBED_MIN_CTAS))
 dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EmbedArgs em, StripGeom sg) {
     constexpr int kStages = kEmbedStages;
     constexpr int kConsumerWarps = kCW;
@@ -397,28 +401,39 @@ dwtsvd_embed_tma_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ d
 
     // ===== consumer warps =====
     const int t = threadIdx.x;                                   // the launcher guarantees chunk_tiles <= 2 * kStripThreads
+    // The watermark bits of a thread's two tiles come from global memory through a dependent chain (the frame's row
+    // number, then the word of that row holding the bit).  Both levels are fetched ahead - the row number two items
+    // ahead, the words one item ahead - so that each load has a whole item's arithmetic to land in: with the chain
+    // inside the item a batch with per-frame rows ran 6 % slower than one with a single row.
+    auto row_of = [&](int i) -> int {
+        if (!em.frame_row || i >= sg.total) return 0;
+        const int frame = (int)(((unsigned long long)(unsigned)i * sg.frame_magic) >> 40);
+        return em.frame_row[frame];
+    };
+    // -> the two words holding the bits of this thread's low / high tile in item i, and the bit positions inside them
+    auto words_of = [&](int i, int row, unsigned& w_lo, unsigned& w_hi) {
+        w_lo = w_hi = 0u;
+        if (i >= sg.total) return;
+        const Item it = item_of<kWhole, kNarrow>(i, sg);
+        const TilePair<kNarrow> tp(t, it, sg, 0u);
+        const uint32_t* wrow = em.wm + (long long)clamp_row(row, em.n_rows) * em.wm_words;
+        const unsigned c = (unsigned)(it.ty * g.tiles_x + it.cx * sg.chunk_tiles + t);
+        const int wi_lo = (int)(c >> 5), wi_hi = (int)((c + tp.hi_delta) >> 5);
+        if (tp.live_lo && wi_lo < em.wm_words) w_lo = wrow[wi_lo];
+        if (tp.live_hi && wi_hi < em.wm_words) w_hi = wrow[wi_hi];
+    };
+    unsigned next_lo, next_hi;
+    words_of((int)blockIdx.x, row_of((int)blockIdx.x), next_lo, next_hi);
+    int row_ahead = row_of((int)blockIdx.x + step);
     for (int i = (int)blockIdx.x; i < sg.total; i += step) {
         const Item it = item_of<kWhole, kNarrow>(i, sg);
         const unsigned slot = ring + stage * sg.slot_bytes;
         const unsigned sp = kPitch ? kPitch : sg.slot_pitch;
         const TilePair<kNarrow> tp(t, it, sg, sp);
-        // the watermark bits of this warp's tiles (32 per half), funnel-shifted out of the packed row;
-        // issued before the wait so that their latency hides behind it
-        const int row = em.frame_row ? clamp_row(em.frame_row[it.frame], em.n_rows) : 0;
-        const uint32_t* wrow = em.wm + (long long)row * em.wm_words;
-        const unsigned c0 = (unsigned)(it.ty * g.tiles_x + it.cx * sg.chunk_tiles + (t & ~31));
-        unsigned wbits[2];
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-            const unsigned c = c0 + hlf * tp.hi_delta;
-            const int wi = (int)(c >> 5);
-            wbits[hlf] = 0u;
-            if (wi < em.wm_words) {
-                const unsigned lo = wrow[wi], hi = (wi + 1 < em.wm_words) ? wrow[wi + 1] : 0u;
-                wbits[hlf] = __funnelshift_r(lo, hi, c & 31u);
-            }
-        }
-        const unsigned mybits = ((wbits[0] >> lane) & 1u) | (((wbits[1] >> lane) & 1u) << 1);
+        const unsigned c = (unsigned)(it.ty * g.tiles_x + it.cx * sg.chunk_tiles + t);
+        const unsigned mybits = ((next_lo >> (c & 31u)) & 1u) | (((next_hi >> ((c + tp.hi_delta) & 31u)) & 1u) << 1);
+        words_of(i + step, row_ahead, next_lo, next_hi);          // issued here, used in the next iteration
+        row_ahead = row_of(i + 2 * step);
         mbar_wait(full0 + 8 * stage, parity);
         {
             const unsigned mine_lo = slot + tp.off_lo, mine_hi = slot + tp.off_hi;
@@ -575,11 +590,11 @@ int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const Til
     const uint8_t* p = (const uint8_t*)src;
     // Wide planes with tight rows (4K: 480 tiles per row): the whole 8-row strip is contiguous, so the extract kernel takes
     // it as ONE 30 KB bulk copy with eight consumer warps (two CTAs per SM) instead of two column chunks moved row by row
-    // (sixteen 1.9 KB copies): 0.86 -> 0.94 of the HBM peak at 4K.  (Embed keeps the chunks: its 128 registers leave no room
-    // for two CTAs of nine warps.)
+    // (sixteen 1.9 KB copies): 0.86 -> 0.94 of the HBM peak at 4K, 0.965 with the row pitch as a compile-time constant.
     if (g.tiles_x > kMaxStripTiles && g.tiles_x <= 2 * kMaxStripTiles && pl->pitch_bytes == 8ll * g.tiles_x) {
         const StripGeom wide = make_strip_geom(g, pl, 2 * kMaxStripTiles);
-        if (wide.whole && wide.total < (1 << 26)) return launch_extract_t<true, false, 0, 8>(p, xa, wide, stream);
+        if (wide.whole && wide.total < (1 << 26))
+            return wide.slot_pitch == 3840 ? launch_extract_t<true, false, 3840, 8>(p, xa, wide, stream) : launch_extract_t<true, false, 0, 8>(p, xa, wide, stream);
     }
     const StripGeom sg = make_strip_geom(g, pl);
     if (sg.narrow) {
@@ -593,9 +608,20 @@ int launch_dwtsvd_extract_tma(const void* src, const b200wm_plane* pl, const Til
 
 int launch_dwtsvd_embed_tma(const void* src, void* dst, const b200wm_plane* pl, const TileGeom& g, EmbedArgs ea,
                             cudaStream_t stream) {
-    const StripGeom sg = make_strip_geom(g, pl);
     const uint8_t* p = (const uint8_t*)src;
     uint8_t* d = (uint8_t*)dst;
+    // The same strip shape as the 4K extract: one 30 KB bulk copy in, one out, eight consumer warps, two CTAs per SM.  Two
+    // CTAs of nine warps leave 96 registers per thread (a handful of spilled words) and still beat the column chunks,
+    // whose strips move as sixteen 1.9 KB row copies: 0.91 -> 0.96 of the HBM peak at 4K (scripts/probe_plane.py).  The
+    // same shape for two tile rows of a 1080p plane was measured too and lost to the four-warp CTAs (0.96 against 0.99).
+    // B200WM_NO_EMBED_WIDE=1 in the environment brings the chunks back (A/B evidence).
+    static const bool wide_embed = getenv("B200WM_NO_EMBED_WIDE") == nullptr;
+    if (wide_embed && g.tiles_x > kMaxStripTiles && g.tiles_x <= 2 * kMaxStripTiles && pl->pitch_bytes == 8ll * g.tiles_x) {
+        const StripGeom wide = make_strip_geom(g, pl, 2 * kMaxStripTiles);
+        if (wide.whole && wide.total < (1 << 26))
+            return wide.slot_pitch == 3840 ? launch_embed_t<true, false, 3840, 8>(p, d, ea, wide, stream) : launch_embed_t<true, false, 0, 8>(p, d, ea, wide, stream);
+    }
+    const StripGeom sg = make_strip_geom(g, pl);
     if (sg.narrow) {
         if (sg.whole) return sg.slot_pitch == 960 ? launch_embed_t<true, true, 960>(p, d, ea, sg, stream) : launch_embed_t<true, true, 0>(p, d, ea, sg, stream);
         return launch_embed_t<false, true, 0>(p, d, ea, sg, stream);
