@@ -59,6 +59,20 @@ def gathered_batches(reader, batch_frames):
         yield pending
 
 
+_LANES = {}
+
+
+def lane_streams(device, n):
+    """``n`` side streams of ``device`` for batches in flight, created once per process: the caching allocator keeps one
+    block pool per stream, so drivers that made their own streams on every ``start()`` paid fresh ``cudaMalloc`` calls
+    for every batch buffer and left the freed blocks stranded in pools nobody used again."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    have = _LANES.setdefault(key, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(device=device))
+    return have[:n]
+
+
 _POOL = None
 
 

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from b200wm import ops
-from .._frames import device_of, gathered_batches, Staging
+from .._frames import device_of, gathered_batches, lane_streams, Staging
 
 logger = logging.getLogger(__name__)
 
@@ -66,7 +66,7 @@ class Embedder:
         written in order and byte-identical to the per-frame path."""
         dev = device_of(self.device)
         main = torch.cuda.current_stream(dev)
-        lanes = [torch.cuda.Stream(device=dev) for _ in range(_LANES)]
+        lanes = lane_streams(dev, _LANES)
         staged = flying = None                 # (slot, pinned host tensor, copy futures) / (event, marked host frames)
         for k, group in enumerate(gathered_batches(self.frame_reader, self.batch_frames)):
             slot = k % _LANES
@@ -106,7 +106,7 @@ class Embedder:
         batch k and the download of batch k-1 overlap; batches are committed to the writer in order."""
         dev = device_of(self.device)
         main = torch.cuda.current_stream(dev)
-        lanes = [torch.cuda.Stream(device=dev) for _ in range(_LANES)]
+        lanes = lane_streams(dev, _LANES)
         inflight = collections.deque()
         k = 0
         while True:

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from b200wm import ops
-from .._frames import device_of, gathered_batches, Staging
+from .._frames import device_of, gathered_batches, lane_streams, Staging
 
 logger = logging.getLogger(__name__)
 
@@ -84,7 +84,7 @@ class Extractor:
         k); patterns are logged in frame order."""
         dev = device_of(self.device)
         main = torch.cuda.current_stream(dev)
-        lanes = [torch.cuda.Stream(device=dev) for _ in range(_LANES)]
+        lanes = lane_streams(dev, _LANES)
         inflight = collections.deque()
         k = 0
         while True:
