@@ -287,3 +287,23 @@ def test_batch_reader_and_writer_bookkeeping():
     w.rewind()
     w.write(frames[4])
     assert len(w.frames) == 1 and np.array_equal(w.frames[0], frames[4])
+
+
+def test_gathered_batches_cut_at_size_and_at_shape_changes():
+    """offmark_b200/_frames.py:gathered_batches - the reference's read() loop (video/embedder.py:19-27) gathered into
+    one-shape batches for the batched drivers."""
+    from offmark_b200._frames import gathered_batches
+    from offmark_b200.video.memory_io import ArrayReader
+    shapes = [(4, 6)] * 4 + [(6, 4)] * 2 + [(4, 6)] * 5
+    frames = [np.full((h, w, 3), k, dtype=np.int64) for k, (h, w) in enumerate(shapes)]
+    got = list(gathered_batches(ArrayReader(frames), 3))
+    assert [len(g) for g in got] == [3, 1, 2, 3, 2]
+    flat = [f for g in got for f in g]
+    assert all(f.dtype == np.uint8 and f.flags["C_CONTIGUOUS"] for f in flat)
+    assert [int(f[0, 0, 0]) for f in flat] == list(range(len(frames))) and [f.shape[:2] for f in flat] == shapes
+    assert list(gathered_batches(ArrayReader(frames[:1]), 8))[0][0].shape == (4, 6, 3)
+
+    class Empty:
+        def read(self):
+            return None
+    assert list(gathered_batches(Empty(), 4)) == []
