@@ -74,6 +74,30 @@ def test_dct8_masks_vs_oracle(golden_dir):
         print(f"{name}: texture mask differs on {n} of {differ.size} blocks, all decision-tree ties")
 
 
+def test_public_mask_methods_of_the_dct_plugins(golden_dir):
+    """``DctEncoder.luminance_mask`` / ``texture_mask`` (dct_encoder.py:41-102; the decoder carries copies,
+    dct_decoder.py:29-89) are public in the reference: same arrays here, float64 ``[H/8, W/8]``, numpy in -> numpy out,
+    strided views of an interleaved frame accepted as the reference passes them (``yuv[:, :, 0]``)."""
+    from offmark_b200.embed.dct_encoder import DctEncoder
+    from offmark_b200.extract.dct_decoder import DctDecoder
+    for name, frame in list(_sources(golden_dir))[:3]:
+        yuv = bracket.to_yuv(frame)
+        _, tex_o, lum_o = _masks_oracle(yuv[:, :, 0])
+        for plugin in (DctEncoder(), DctDecoder()):
+            lum = plugin.luminance_mask(yuv[:, :, 0])
+            tex = plugin.texture_mask(yuv[:, :, 0])
+            assert isinstance(lum, np.ndarray) and lum.dtype == np.float64 and lum.shape == lum_o.shape == tex.shape
+            # the brightness rule is continuous but for its two steps at 15 and 25: a block mean within float32 rounding
+            # of a step may land on the other side
+            near_step = np.isclose(_masks_oracle(yuv[:, :, 0])[0], 15, atol=1e-4) | np.isclose(_masks_oracle(yuv[:, :, 0])[0], 25, atol=1e-4)
+            assert np.allclose(lum[~near_step], lum_o[~near_step], rtol=1e-6, atol=1e-6), name
+            _explained(~np.isclose(tex, tex_o, rtol=2e-5, atol=1e-6), o_dct.tie_blocks(yuv)["mask"], f"texture_mask(), {name}")
+        on_device = DctEncoder().texture_mask(torch.from_numpy(yuv).to(DEV)[:, :, 0])
+        assert on_device.is_cuda and np.array_equal(on_device.cpu().numpy(), tex)
+    with pytest.raises(ValueError):
+        DctEncoder().luminance_mask(np.zeros((16, 16)))
+
+
 @pytest.mark.parametrize("source", ["frame63 crop", "synthetic 128x192", "synthetic 100x132 (ragged)", "1080p (fixture tiled + noise)"])
 def test_dct8_embed_extract_vs_oracle(golden_dir, source):
     """DctEncoder.encode / DctDecoder.decode on the reference's float32 interleaved layout: marked channel within 2e-3

@@ -1,0 +1,66 @@
+"""CPU, this container only: the drop-in classes keep the reference's call surface.
+
+The reference's sources are parsed (not imported: two of its modules need PyWavelets) and every public method of every
+mirrored class is compared with the class of the same name under ``offmark_b200``: same method names, same positional
+parameters in the same order with the same defaults; the B200 classes may only ADD trailing parameters that have
+defaults (``device``, ``batch_frames``).  Skipped where the reference checkout is absent (the GPU box)."""
+import ast
+import importlib
+import inspect
+import os
+
+import pytest
+
+REFERENCE = os.path.join(os.sep, "root", "reference", "src", "offmark")
+MIRRORED = {                                   # module path under offmark / offmark_b200 -> class
+    "embed.dwt_dct_svd_encoder": "DwtDctSvdEncoder", "embed.dct_encoder": "DctEncoder",
+    "extract.dwt_dct_svd_decoder": "DwtDctSvdDecoder", "extract.dct_decoder": "DctDecoder",
+    "generator.shuffler": "Shuffler", "generator.grayscale": "GrayScale",
+    "degenerator.de_shuffler": "DeShuffler", "degenerator.de_grayscale": "DeGrayScale",
+    "video.embedder": "Embedder", "video.extractor": "Extractor",
+}
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+
+
+def _reference_methods(module, cls_name):
+    """{method name: [(parameter, default or inspect.Parameter.empty), ...]} of the class as written in the reference."""
+    tree = ast.parse(open(os.path.join(REFERENCE, *module.split(".")) + ".py").read())
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == cls_name)
+    out = {}
+    for fn in cls.body:
+        if not isinstance(fn, ast.FunctionDef):
+            continue
+        name = fn.name
+        if name.startswith("_" + cls_name + "__") or (name.startswith("__") and name != "__init__"):
+            continue                           # name-mangled privates (self.__encode_frame ...)
+        if name.startswith("_") and name != "__init__":
+            continue
+        params = [a.arg for a in fn.args.args][1:]                  # without self
+        defaults = [inspect.Parameter.empty] * (len(params) - len(fn.args.defaults)) + \
+                   [ast.literal_eval(d) for d in fn.args.defaults]
+        out[name] = list(zip(params, defaults))
+    return out
+
+
+@pytest.mark.parametrize("module", sorted(MIRRORED))
+def test_class_surface_equals_the_reference(module):
+    cls_name = MIRRORED[module]
+    want = _reference_methods(module, cls_name)
+    assert "__init__" in want or cls_name in ("Embedder", "Extractor")
+    ours = getattr(importlib.import_module("offmark_b200." + module), cls_name)
+    for name, ref_params in want.items():
+        fn = getattr(ours, name, None)
+        assert callable(fn), f"{cls_name}.{name} is missing"
+        got = [(p.name, p.default) for p in list(inspect.signature(fn).parameters.values())[1:]
+               if p.kind in (p.POSITIONAL_OR_KEYWORD, p.POSITIONAL_ONLY)]
+        assert got[:len(ref_params)] == ref_params, f"{cls_name}.{name}: {got} vs reference {ref_params}"
+        for extra, default in got[len(ref_params):]:
+            assert default is not inspect.Parameter.empty, f"{cls_name}.{name}: added parameter {extra} needs a default"
+
+
+def test_every_mirrored_module_is_listed_by_the_package():
+    import offmark_b200
+    listed = set(getattr(offmark_b200, "MIRRORED_MODULES", ()))
+    if listed:
+        assert {m for m in MIRRORED} <= {m.replace("offmark_b200.", "").replace("offmark.", "") for m in listed}

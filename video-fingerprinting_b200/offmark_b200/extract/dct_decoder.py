@@ -3,10 +3,11 @@ import numpy as np
 
 from b200wm import ops
 from .._frames import FrameOnDevice
+from .._dct_masks import DctMasks
 
 
-class DctDecoder:
-    """Same constructor and ``decode`` as the reference class (dct_decoder.py:4-27)."""
+class DctDecoder(DctMasks):
+    """Same constructor, ``decode`` and public mask methods as the reference class (dct_decoder.py:4-89)."""
 
     def __init__(self, key=None, alpha=20, device=None):
         self.key = key
