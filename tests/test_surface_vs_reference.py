@@ -59,6 +59,25 @@ def test_class_surface_equals_the_reference(module):
             assert default is not inspect.Parameter.empty, f"{cls_name}.{name}: added parameter {extra} needs a default"
 
 
+@pytest.mark.parametrize("module", sorted(MIRRORED))
+def test_instances_carry_the_attributes_the_reference_sets_in_init(module):
+    """``self.key``, ``self.scales``, ``self.frame_reader`` ...: scripts built on the reference read them."""
+    cls_name = MIRRORED[module]
+    tree = ast.parse(open(os.path.join(REFERENCE, *module.split(".")) + ".py").read())
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == cls_name)
+    init = next((f for f in cls.body if isinstance(f, ast.FunctionDef) and f.name == "__init__"), None)
+    if init is None:
+        pytest.skip("no __init__ in the reference class")
+    attrs = {t.attr for n in ast.walk(init) if isinstance(n, ast.Assign) for t in n.targets
+             if isinstance(t, ast.Attribute) and isinstance(t.value, ast.Name) and t.value.id == "self"
+             and not t.attr.startswith("_")}
+    ours = getattr(importlib.import_module("offmark_b200." + module), cls_name)
+    required = [p for p in list(inspect.signature(ours.__init__).parameters.values())[1:] if p.default is p.empty]
+    obj = ours(*[None] * len(required))
+    missing = sorted(a for a in attrs if not hasattr(obj, a))
+    assert not missing, f"{cls_name} lacks attributes the reference sets: {missing}"
+
+
 def test_every_mirrored_module_is_listed_by_the_package():
     import offmark_b200
     listed = set(getattr(offmark_b200, "MIRRORED_MODULES", ()))
