@@ -78,6 +78,48 @@ def test_instances_carry_the_attributes_the_reference_sets_in_init(module):
     assert not missing, f"{cls_name} lacks attributes the reference sets: {missing}"
 
 
+def _reference_module(module):
+    """One reference module loaded from its file (no package import: offmark/__init__ pulls in ffmpeg bindings)."""
+    import importlib.util
+    path = os.path.join(REFERENCE, *module.split(".")) + ".py"
+    spec = importlib.util.spec_from_file_location("reference_" + module.replace(".", "_"), path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_generators_equal_the_reference_on_random_payloads():
+    """generator/shuffler.py:15-25, generator/grayscale.py:16-31 run live next to the host-side mirrors."""
+    import warnings
+
+    import numpy as np
+    from offmark_b200.generator.shuffler import Shuffler
+    from offmark_b200.generator.grayscale import GrayScale
+    ref_s, ref_g = _reference_module("generator.shuffler").Shuffler, _reference_module("generator.grayscale").GrayScale
+    rng = np.random.RandomState(5)
+    for key in (None, 0, 7, 123456):
+        for length, capacity in ((8, (1, 32400)), (8, (1, 5)), (13, (1, 1200)), (1, (1, 9)), (64, (3, 100)), (40, (1, 40))):
+            payload = rng.randint(0, 2, length)
+            keep = payload.copy()
+            if key is None:                     # unseeded: only shapes, dtypes and the multiset of bits can agree
+                a = Shuffler().generate_wm(payload, capacity)
+                assert a.shape == tuple(capacity) and a.dtype == ref_s().generate_wm(payload, capacity).dtype
+                continue
+            a, b = Shuffler(key=key).generate_wm(payload, capacity), ref_s(key=key).generate_wm(payload, capacity)
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+            assert np.array_equal(payload, keep)                 # neither mutates its argument
+        for shape, capacity in (((4, 6), (1, 100)), ((9, 9), (1, 50)), ((2, 2), (1, 4))):
+            image = rng.randint(0, 256, shape).astype(np.uint8)
+            with warnings.catch_warnings(record=True) as w_ours:
+                warnings.simplefilter("always")
+                a = GrayScale(key=key or 0).generate_wm(image, capacity)
+            with warnings.catch_warnings(record=True) as w_ref:
+                warnings.simplefilter("always")
+                b = ref_g(key=key or 0).generate_wm(image, capacity)
+            assert a.dtype == b.dtype and np.array_equal(a, b) and len(w_ours) == len(w_ref)
+    assert Shuffler.wm_type() == ref_s.wm_type() and GrayScale.wm_type() == ref_g.wm_type()
+
+
 def test_every_mirrored_module_is_listed_by_the_package():
     import offmark_b200
     listed = set(getattr(offmark_b200, "MIRRORED_MODULES", ()))
