@@ -59,7 +59,7 @@ def gathered_batches(reader, batch_frames):
         yield pending
 
 
-_LANES = {}
+_LANE_STREAMS = {}
 
 
 def lane_streams(device, n):
@@ -67,7 +67,7 @@ def lane_streams(device, n):
     block pool per stream, so drivers that made their own streams on every ``start()`` paid fresh ``cudaMalloc`` calls
     for every batch buffer and left the freed blocks stranded in pools nobody used again."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    have = _LANES.setdefault(key, [])
+    have = _LANE_STREAMS.setdefault(key, [])
     while len(have) < n:
         have.append(torch.cuda.Stream(device=device))
     return have[:n]
